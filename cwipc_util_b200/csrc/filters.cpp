@@ -1,0 +1,243 @@
+// filters.cpp -- the C-ABI filter entry points: argument rules, cellsize/timestamp propagation,
+// per-tile grouping and error behaviour of the reference, with the arithmetic done by the CUDA
+// kernels in pointops.cu / downsample.cu / outliers.cu.
+// ref: src/cwipc_filters.cpp:30-418
+#include <algorithm>
+#include <cstring>
+
+#include "kernels.hpp"
+#include "pointcloud.hpp"
+
+using namespace cwcu;
+
+namespace {
+
+// Common shape of a one-input filter: resolve storage, run `body(in, dev, stream)` -> StoragePtr,
+// wrap the result with the input's timestamp and the given cellsize.
+template <class Body>
+cwipc_pointcloud *unary_filter(const char *who, cwipc_pointcloud *pc, Body &&body) {
+    if (pc == nullptr) return nullptr; // ref: src/cwipc_filters.cpp:282-284 (silent)
+    return guarded<cwipc_pointcloud *>(who, nullptr, [&]() -> cwipc_pointcloud * {
+        StoragePtr in = storage_of(pc, who);
+        if (!in) return nullptr;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        StoragePtr out;
+        try {
+            out = body(in, in->dev, s);
+        } catch (...) {
+            in->release_after_read(s);
+            throw;
+        }
+        in->release_after_read(s);
+        if (!out) return nullptr;
+        auto *rv = new DevicePointcloud(out, pc->timestamp(), 0.f);
+        rv->_set_cellsize(pc->cellsize());
+        return rv;
+    });
+}
+
+StoragePtr compact_to_new(const StoragePtr &in, const Predicate &pred, int dev, cudaStream_t s) {
+    auto out = std::make_shared<Storage>(dev, in->count, s);
+    out->count = compact_points(in->d_pts, in->count, out->d_pts, pred, dev, s);
+    out->mark_ready();
+    return out;
+}
+
+} // namespace
+
+extern "C" {
+
+// keep iff tile == 0 || point.tile == tile; stable; empty in -> empty out.  ref: src/cwipc_filters.cpp:281-306
+cwipc_pointcloud *cwipc_tilefilter(cwipc_pointcloud *pc, int tile) {
+    return unary_filter("cwipc_tilefilter", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        if (tile == 0) return in; // keeps every point: storage is immutable, so share it
+        if (tile < 0 || tile > 255) {
+            // `tile == pt.a` with an 8-bit pt.a can never hold: empty result
+            auto out = std::make_shared<Storage>(dev, 0, s);
+            out->mark_ready();
+            return out;
+        }
+        Predicate p;
+        p.kind = PredKind::TileEquals;
+        p.tile = tile;
+        return compact_to_new(in, p, dev, s);
+    });
+}
+
+// (tile & mask) != 0, the variant python/cwipc/registration/util.py:98-112 builds in numpy
+cwipc_pointcloud *cwipc_cuda_tilefilter_masked(cwipc_pointcloud *pc, int mask) {
+    return unary_filter("cwipc_tilefilter_masked", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        Predicate p;
+        p.kind = PredKind::TileMask;
+        p.tile = mask & 0xff;
+        return compact_to_new(in, p, dev, s);
+    });
+}
+
+// ref: src/cwipc_filters.cpp:333-360
+cwipc_pointcloud *cwipc_crop(cwipc_pointcloud *pc, float bbox[6]) {
+    return unary_filter("cwipc_crop", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        Predicate p;
+        p.kind = PredKind::CropBox;
+        memcpy(p.box, bbox, sizeof(p.box));
+        return compact_to_new(in, p, dev, s);
+    });
+}
+
+// ref: src/cwipc_filters.cpp:308-331
+cwipc_pointcloud *cwipc_tilemap(cwipc_pointcloud *pc, uint8_t map[256]) {
+    return unary_filter("cwipc_tilemap", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        auto out = std::make_shared<Storage>(dev, in->count, s);
+        out->count = in->count;
+        tilemap_points(in->d_pts, in->count, out->d_pts, map, s);
+        out->mark_ready();
+        return out;
+    });
+}
+
+// ref: src/cwipc_filters.cpp:362-386
+cwipc_pointcloud *cwipc_colormap(cwipc_pointcloud *pc, uint32_t clearBits, uint32_t setBits) {
+    return unary_filter("cwipc_colormap", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        auto out = std::make_shared<Storage>(dev, in->count, s);
+        out->count = in->count;
+        colormap_points(in->d_pts, in->count, out->d_pts, clearBits, setBits, s);
+        out->mark_ready();
+        return out;
+    });
+}
+
+// concatenation; timestamp and cellsize are the minima.  ref: src/cwipc_filters.cpp:388-418
+cwipc_pointcloud *cwipc_join(cwipc_pointcloud *pc1, cwipc_pointcloud *pc2) {
+    if (pc1 == nullptr || pc2 == nullptr) return nullptr;
+    return guarded<cwipc_pointcloud *>("cwipc_join", nullptr, [&]() -> cwipc_pointcloud * {
+        StoragePtr a = storage_of(pc1, "cwipc_join"), b = storage_of(pc2, "cwipc_join");
+        if (!a || !b) return nullptr;
+        const int dev = a->dev;
+        DeviceGuard g(dev);
+        cudaStream_t s = thread_stream(dev);
+        a->acquire_for_read(s);
+        b->acquire_for_read(s);
+        auto out = std::make_shared<Storage>(dev, a->count + b->count, s);
+        out->count = a->count + b->count;
+        if (a->count) CWCU_CHECK(cudaMemcpyAsync(out->d_pts, a->d_pts, a->count * sizeof(cwipc_point), cudaMemcpyDeviceToDevice, s));
+        if (b->count) {
+            // a cloud on another device is reachable through peer copy (UVA)
+            CWCU_CHECK(cudaMemcpyAsync(out->d_pts + a->count, b->d_pts, b->count * sizeof(cwipc_point), cudaMemcpyDefault, s));
+        }
+        out->mark_ready();
+        a->release_after_read(s);
+        b->release_after_read(s);
+        auto *rv = new DevicePointcloud(out, std::min(pc1->timestamp(), pc2->timestamp()), 0.f);
+        rv->_set_cellsize(std::min(pc1->cellsize(), pc2->cellsize()));
+        return rv;
+    });
+}
+
+// Voxel-grid downsample.  voxelsize > 0: the reference's octree-split path (a grid per 64-voxel
+// octree leaf, so voxels cut by a leaf face come out once per leaf); voxelsize < 0: one global grid.
+// The cloud's own cellsize wins when it is larger.  ref: src/cwipc_filters.cpp:30-172
+cwipc_pointcloud *cwipc_downsample(cwipc_pointcloud *pc, float voxelsize) {
+    if (pc == nullptr) return nullptr;
+    const bool octree_split = !(voxelsize < 0);
+    float cellsize = octree_split ? voxelsize : -voxelsize;
+    return guarded<cwipc_pointcloud *>("cwipc_downsample", nullptr, [&]() -> cwipc_pointcloud * {
+        const float old = pc->cellsize();
+        if (old >= cellsize) cellsize = old; // ref: :42-46, :103-107
+        StoragePtr in = storage_of(pc, "cwipc_downsample");
+        if (!in) return nullptr;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        DownsampleResult r;
+        try {
+            r = downsample_points(in, cellsize, octree_split, in->dev, s);
+        } catch (...) {
+            in->release_after_read(s);
+            throw;
+        }
+        in->release_after_read(s);
+        if (r.failed || !r.out) {
+            log(CWIPC_LOG_LEVEL_ERROR, "cwipc_downsample", r.error.empty() ? std::string("downsample failed") : r.error);
+            return nullptr;
+        }
+        auto *rv = new DevicePointcloud(r.out, pc->timestamp(), 0.f);
+        rv->_set_cellsize(cellsize);
+        return rv;
+    });
+}
+
+// Statistical outlier removal, whole cloud or once per distinct tile value (first-appearance order,
+// tile 0 meaning "every point" exactly as cwipc_tilefilter(pc, 0) does).  ref: src/cwipc_filters.cpp:181-278
+cwipc_pointcloud *cwipc_remove_outliers(cwipc_pointcloud *pc, int kNeighbors, float stddevMulThresh, bool perTile) {
+    return unary_filter("cwipc_remove_outliers", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        const float spacing = pc->cellsize();
+        const size_t n = in->count;
+        if (!perTile) {
+            auto out = std::make_shared<Storage>(dev, n, s);
+            out->count = remove_outliers_points(in->d_pts, n, out->d_pts, kNeighbors, stddevMulThresh, spacing, dev, s);
+            out->mark_ready();
+            return out;
+        }
+        std::vector<int> tiles = tiles_in_first_appearance_order(in->d_pts, n, s);
+        const bool has_zero = std::find(tiles.begin(), tiles.end(), 0) != tiles.end();
+        auto out = std::make_shared<Storage>(dev, has_zero ? 2 * n : n, s);
+        Scratch group(n * sizeof(cwipc_point), s);
+        size_t total = 0;
+        for (int tile : tiles) {
+            const cwipc_point *src = in->d_pts;
+            size_t cnt = n;
+            if (tile != 0) {
+                Predicate p;
+                p.kind = PredKind::TileEquals;
+                p.tile = tile;
+                cnt = compact_points(in->d_pts, n, group.as<cwipc_point>(), p, dev, s);
+                src = group.as<cwipc_point>();
+            }
+            total += remove_outliers_points(src, cnt, out->d_pts + total, kNeighbors, stddevMulThresh, spacing, dev, s);
+        }
+        out->count = total;
+        out->mark_ready();
+        return out;
+    });
+}
+
+// ---- diagnostic hooks used by the parity tests ---------------------------------------------------
+int cwipc_cuda_knn_mean_distances(cwipc_pointcloud *pc, int kNeighbors, float *dist, size_t ndist) {
+    if (pc == nullptr || dist == nullptr) return -1;
+    return guarded<int>("cwipc_cuda_knn_mean_distances", -1, [&]() -> int {
+        StoragePtr in = storage_of(pc, "cwipc_cuda_knn_mean_distances");
+        if (!in || ndist < in->count) return -1;
+        if (in->count == 0) return 0;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        Scratch d(in->count * sizeof(float), s);
+        knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), d.as<float>(), in->dev, s);
+        CWCU_CHECK(cudaMemcpyAsync(dist, d.p, in->count * sizeof(float), cudaMemcpyDeviceToHost, s));
+        in->release_after_read(s);
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        return (int)in->count;
+    });
+}
+
+int cwipc_cuda_downsample_keys(cwipc_pointcloud *pc, float voxelsize, uint64_t *keys, size_t nkeys) {
+    if (pc == nullptr || keys == nullptr) return -1;
+    return guarded<int>("cwipc_cuda_downsample_keys", -1, [&]() -> int {
+        StoragePtr in = storage_of(pc, "cwipc_cuda_downsample_keys");
+        if (!in || nkeys < in->count) return -1;
+        if (in->count == 0) return 0;
+        const bool octree_split = !(voxelsize < 0);
+        float cellsize = octree_split ? voxelsize : -voxelsize;
+        if (pc->cellsize() >= cellsize) cellsize = pc->cellsize();
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        downsample_keys_to_host(in, cellsize, octree_split, keys, in->dev, s);
+        in->release_after_read(s);
+        return (int)in->count;
+    });
+}
+
+} // extern "C"

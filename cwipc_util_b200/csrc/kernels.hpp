@@ -1,0 +1,54 @@
+// kernels.hpp -- host-callable launchers of the filter kernels.  All work is queued on the given
+// stream; functions that return a count synchronise that stream once to read it back.
+#pragma once
+
+#include "runtime.hpp"
+
+namespace cwcu {
+
+// ---- pointops.cu: stable compaction and per-point maps -------------------------------------
+enum class PredKind : int { TileEquals = 0, TileMask = 1, CropBox = 2, DistanceAtMost = 3 };
+
+struct Predicate {
+    PredKind kind = PredKind::TileEquals;
+    int tile = 0;                 // TileEquals (0 keeps everything) / TileMask
+    float box[6] = {0, 0, 0, 0, 0, 0}; // CropBox: minx,maxx,miny,maxy,minz,maxz
+    const float *dist = nullptr;  // DistanceAtMost: keep iff !(dist[i] > threshold)
+    double threshold = 0.0;
+};
+
+// Stable compaction of in[0..n) by `pred` into out (capacity >= n).  Returns the number kept.
+size_t compact_points(const cwipc_point *in, size_t n, cwipc_point *out, const Predicate &pred, int dev, cudaStream_t s);
+
+void tilemap_points(const cwipc_point *in, size_t n, cwipc_point *out, const uint8_t map[256], cudaStream_t s);
+void colormap_points(const cwipc_point *in, size_t n, cwipc_point *out, uint32_t clearBits, uint32_t setBits, cudaStream_t s);
+// min over i>=1 of |p_i - p_0| (float), 0 when n < 2.  ref: src/cwipc_util.cpp:173-204
+float min_distance_to_first(const cwipc_point *in, size_t n, cudaStream_t s);
+// distinct tile values in first-appearance order. ref: src/cwipc_filters.cpp:239-249
+std::vector<int> tiles_in_first_appearance_order(const cwipc_point *in, size_t n, cudaStream_t s);
+
+// ---- downsample.cu -------------------------------------------------------------------------
+struct DownsampleResult {
+    StoragePtr out;    // nullptr on failure
+    bool failed = false;
+    std::string error; // reference-compatible error text when failed
+};
+// cellsize > 0 already resolved against the cloud's own cellsize.  octree_split selects the
+// reference's positive-size path (per-octree-leaf grids) vs the single global grid.
+DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool octree_split, int dev, cudaStream_t s);
+// global bounding box of in[0..n), n > 0 (synchronises the stream)
+void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], int dev, cudaStream_t s);
+// diagnostic: sort keys (without the index bits) per input point, to host
+void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_split, uint64_t *host_keys, int dev, cudaStream_t s);
+
+// ---- outliers.cu ---------------------------------------------------------------------------
+// Statistical outlier removal on in[0..n) (one group).  Appends survivors to out (capacity >= n),
+// returns the number kept.  `hint_spacing` is the cloud's cellsize (0 if unknown).
+size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, int dev, cudaStream_t s);
+// First pass only: mean distance to the k nearest neighbours per point, original order, device array.
+void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, float *d_dist, int dev, cudaStream_t s);
+
+// ---- runtime.cu ----------------------------------------------------------------------------
+void flush_l2(int dev, cudaStream_t s);
+
+} // namespace cwcu

@@ -1,0 +1,232 @@
+// radix_sort.cu -- stable LSD radix sort of 64-bit words, 8-bit digits, one read + one write of the
+// data per digit ("onesweep": the digit histograms of every pass are taken up front in one read; each
+// pass ranks a 4096-key tile with warp match_any, chains tiles by decoupled look-back per digit and
+// scatters through shared memory so that global stores are run-contiguous).
+//
+// It replaces boost::sort::spreadsort inside pcl::VoxelGrid (call sites src/cwipc_filters.cpp:52-56,
+// 135-140) and provides the uniform-grid ordering for the kNN of cwipc_remove_outliers.
+// The words carry the point index in their low bits, below begin_bit, so no separate payload moves.
+//
+// HBM-bound: per pass 8 B read + 8 B written per key (+ 8 B per key once for the histograms).
+#include "radix_sort.hpp"
+
+#include "device_utils.cuh"
+
+namespace cwcu {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS; // 4096 keys = 32 KB
+constexpr int RS_BINS = 256;
+constexpr int RS_MAX_PASSES = 8;
+
+constexpr uint32_t ST_FLAG_SHIFT = 30;
+constexpr uint32_t ST_VALUE_MASK = (1u << 30) - 1;
+constexpr uint32_t ST_AGGREGATE = 1u << 30, ST_PREFIX = 2u << 30;
+
+__device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, uint32_t mask) { return (uint32_t)(key >> shift) & mask; }
+
+// Digit histograms of all passes in one read.  Equal digits in neighbouring lanes (the common case for
+// the high digits of spatial keys) are merged with one ballot before touching shared memory.
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int begin_bit, int end_bit, int npasses,
+                                                                 uint32_t *__restrict__ hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * RS_BINS];
+    for (int i = threadIdx.x; i < npasses * RS_BINS; i += RS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned lane = lane_id();
+    const uint32_t stride = gridDim.x * RS_THREADS;
+    for (uint32_t base = blockIdx.x * RS_THREADS; base < n; base += stride) {
+        const uint32_t idx = base + threadIdx.x;
+        const bool valid = idx < n;
+        const uint64_t key = valid ? keys[idx] : 0ull;
+        for (int p = 0; p < npasses; p++) {
+            const int shift = begin_bit + 8 * p;
+            const int bits = min(8, end_bit - shift);
+            const uint32_t d = valid ? digit_of(key, shift, (1u << bits) - 1u) : 0x100u;
+            const uint32_t prev = __shfl_up_sync(FULL_MASK, d, 1);
+            const bool head = (lane == 0) || (d != prev);
+            const unsigned heads = __ballot_sync(FULL_MASK, head);
+            if (head && valid) {
+                const unsigned above = heads & ~((2u << lane) - 1u);
+                const int next = above ? (__ffs(above) - 1) : 32;
+                atomicAdd(&s_hist[p * RS_BINS + d], (uint32_t)(next - (int)lane));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npasses * RS_BINS; i += RS_THREADS) {
+        const uint32_t v = s_hist[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
+// One block per pass: exclusive scan of its 256 digit counts -> first output slot of each digit.
+__global__ void __launch_bounds__(RS_BINS) radix_scan_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ binbase) {
+    __shared__ uint32_t s_warp[RS_BINS / 32];
+    const int p = blockIdx.x;
+    const uint32_t v = hist[p * RS_BINS + threadIdx.x];
+    const uint32_t incl = warp_inclusive_scan(v);
+    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t offset = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) offset += s_warp[w];
+    binbase[p * RS_BINS + threadIdx.x] = offset + incl - v;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint32_t n, int shift, int bits,
+                                                                     const uint32_t *__restrict__ binbase, uint32_t *__restrict__ ticket, uint32_t *__restrict__ status) {
+    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_BINS]; // counts, then exclusive offsets across warps
+    __shared__ uint32_t s_bin_excl[RS_BINS];            // first staging slot of each digit
+    __shared__ uint32_t s_bin_out[RS_BINS];             // global slot of staging slot 0 of each digit (biased)
+    __shared__ uint32_t s_scan[RS_WARPS];
+    __shared__ uint64_t s_keys[RS_TILE];
+    __shared__ int s_tile;
+
+    if (threadIdx.x == 0) s_tile = take_ticket(ticket);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) s_warp_hist[w][threadIdx.x] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+    const uint32_t tile_base = (uint32_t)tile * RS_TILE;
+    if (tile_base >= n) return;
+    const uint32_t tile_count = min((uint32_t)RS_TILE, n - tile_base);
+
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t mask = (1u << bits) - 1u;
+    const uint32_t warp_base = tile_base + warp * (32 * RS_ITEMS);
+
+    // ---- load (warp-striped: memory order == (item, lane) order inside each warp) ----
+    uint64_t key[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        key[i] = idx < n ? in[idx] : ~0ull;
+    }
+
+    // ---- rank inside the warp, digit by digit row ----
+    uint32_t rank[RS_ITEMS];
+    uint32_t *my_hist = s_warp_hist[warp];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t d = valid ? digit_of(key[i], shift, mask) : 0x100u;
+        const unsigned peers = __match_any_sync(FULL_MASK, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if ((int)lane == leader && valid) {
+            before = my_hist[d];
+            my_hist[d] = before + __popc(peers);
+        }
+        before = __shfl_sync(FULL_MASK, before, leader);
+        rank[i] = before + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit (thread == digit): offsets across warps, tile count, chained prefix over tiles ----
+    const uint32_t d = threadIdx.x;
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) {
+        const uint32_t c = s_warp_hist[w][d];
+        s_warp_hist[w][d] = count;
+        count += c;
+    }
+    uint32_t exclusive = 0;
+    {
+        uint32_t *mine = status + (size_t)tile * RS_BINS + d;
+        if (tile == 0) {
+            st_volatile_u32(mine, ST_PREFIX | count);
+        } else {
+            st_volatile_u32(mine, ST_AGGREGATE | count);
+            int t = tile - 1;
+            while (true) {
+                uint32_t s;
+                do {
+                    s = ld_volatile_u32(status + (size_t)t * RS_BINS + d);
+                } while ((s >> ST_FLAG_SHIFT) == 0u);
+                exclusive += s & ST_VALUE_MASK;
+                if ((s >> ST_FLAG_SHIFT) == 2u) break;
+                --t;
+            }
+            st_volatile_u32(mine, ST_PREFIX | (exclusive + count));
+        }
+    }
+    // block-wide exclusive scan of the digit counts -> staging layout
+    {
+        const uint32_t incl = warp_inclusive_scan(count);
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        uint32_t offset = 0;
+        for (int w = 0; w < (int)warp; w++) offset += s_scan[w];
+        const uint32_t excl_in_tile = offset + incl - count;
+        s_bin_excl[d] = excl_in_tile;
+        s_bin_out[d] = binbase[d] + exclusive - excl_in_tile;
+    }
+    __syncthreads();
+
+    // ---- stage: keys land in shared memory grouped by digit, original order inside a digit ----
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; i++) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        if (idx < n) {
+            const uint32_t dd = digit_of(key[i], shift, mask);
+            s_keys[s_bin_excl[dd] + my_hist[dd] + rank[i]] = key[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- scatter: consecutive threads write consecutive slots of a digit's run ----
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; j++) {
+        const uint32_t p = j * RS_THREADS + threadIdx.x;
+        if (p < tile_count) {
+            const uint64_t k = s_keys[p];
+            out[s_bin_out[digit_of(k, shift, mask)] + p] = k;
+        }
+    }
+}
+
+} // namespace
+
+uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int end_bit, int dev, cudaStream_t s) {
+    if (n <= 1 || end_bit <= begin_bit) return a;
+    if (n >= (1u << 30)) throw CudaError{cudaErrorInvalidValue, "radix_sort_u64: more than 2^30 points are not supported"};
+    const int npasses = (end_bit - begin_bit + 7) / 8;
+    if (npasses > RS_MAX_PASSES) throw CudaError{cudaErrorInvalidValue, "radix_sort_u64: bit range too wide"};
+    const size_t ntiles = div_up(n, RS_TILE);
+
+    // [hist P*256 | binbase P*256 | tickets 8 | status P*ntiles*256] (u32 each)
+    const size_t hist_words = (size_t)npasses * RS_BINS;
+    const size_t status_words = (size_t)npasses * ntiles * RS_BINS;
+    const size_t words = 2 * hist_words + 8 + status_words;
+    Scratch scratch(words * sizeof(uint32_t), s);
+    CWCU_CHECK(cudaMemsetAsync(scratch.p, 0, words * sizeof(uint32_t), s));
+    uint32_t *hist = scratch.as<uint32_t>();
+    uint32_t *binbase = hist + hist_words;
+    uint32_t *tickets = binbase + hist_words;
+    uint32_t *status = tickets + 8;
+
+    const unsigned hist_grid = (unsigned)std::max<size_t>(1, std::min(div_up(n, (size_t)RS_THREADS * 8), (size_t)sm_count(dev) * 8));
+    launch("radix_hist_kernel", s, [&] { radix_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(a, (uint32_t)n, begin_bit, end_bit, npasses, hist); });
+    launch("radix_scan_kernel", s, [&] { radix_scan_kernel<<<npasses, RS_BINS, 0, s>>>(hist, binbase); });
+
+    uint64_t *src = a, *dst = b;
+    for (int p = 0; p < npasses; p++) {
+        const int shift = begin_bit + 8 * p;
+        const int bits = std::min(8, end_bit - shift);
+        launch("radix_onesweep_kernel", s, [&] {
+            radix_onesweep_kernel<<<(unsigned)ntiles, RS_THREADS, 0, s>>>(src, dst, (uint32_t)n, shift, bits, binbase + (size_t)p * RS_BINS, tickets + p,
+                                                                           status + (size_t)p * ntiles * RS_BINS);
+        });
+        std::swap(src, dst);
+    }
+    return src;
+}
+
+} // namespace cwcu

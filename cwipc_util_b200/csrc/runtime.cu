@@ -1,0 +1,338 @@
+// runtime.cu -- streams, memory pool, storage lifetime, launch accounting.  See runtime.hpp.
+#include "runtime.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+namespace cwcu {
+
+void throw_cuda(cudaError_t e, const char *expr, const char *file, int line) {
+    std::ostringstream os;
+    os << "CUDA error " << (int)e << " (" << cudaGetErrorName(e) << ": " << cudaGetErrorString(e) << ") at " << file << ":" << line << " in " << expr;
+    throw CudaError{e, os.str()};
+}
+
+// ------------------------------------------------------------------------------------------
+// devices
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct DeviceState {
+    std::once_flag once;
+    int sm_count = 0;
+    std::mutex mu;
+    std::vector<cudaStream_t> idle_streams; // streams returned by exited threads
+};
+
+int g_ndev = -1;
+std::once_flag g_ndev_once;
+DeviceState *g_devs = nullptr;
+
+void init_devices() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        n = 0;
+    }
+    g_devs = new DeviceState[n > 0 ? n : 1];
+    g_ndev = n;
+}
+
+void init_device(int dev) {
+    DeviceState &st = g_devs[dev];
+    std::call_once(st.once, [&] {
+        DeviceGuard g(dev);
+        cudaDeviceProp prop;
+        CWCU_CHECK(cudaGetDeviceProperties(&prop, dev));
+        st.sm_count = prop.multiProcessorCount;
+        // keep freed blocks cached in the pool: steady-state frames never hit cudaMalloc
+        cudaMemPool_t pool;
+        CWCU_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t threshold = UINT64_MAX;
+        CWCU_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    });
+}
+
+int default_device() {
+    const char *env = getenv("CWIPC_CUDA_DEVICE");
+    if (env && *env) return atoi(env);
+    return 0;
+}
+
+struct ThreadState {
+    int device = -1; // -1: not chosen yet
+    std::vector<cudaStream_t> streams; // per device
+    void *pinned = nullptr;
+    size_t pinned_size = 0;
+    ~ThreadState() {
+        // give streams back so that thread churn does not leak them
+        if (g_devs) {
+            for (size_t d = 0; d < streams.size(); d++) {
+                if (streams[d]) {
+                    std::lock_guard<std::mutex> lk(g_devs[d].mu);
+                    g_devs[d].idle_streams.push_back(streams[d]);
+                }
+            }
+        }
+        // the pinned scratch is deliberately not freed: the CUDA runtime may already be gone
+    }
+};
+thread_local ThreadState t_state;
+
+} // namespace
+
+int device_count() {
+    std::call_once(g_ndev_once, init_devices);
+    return g_ndev;
+}
+
+int current_device() {
+    if (t_state.device < 0) t_state.device = default_device();
+    return t_state.device;
+}
+
+bool set_current_device(int dev) {
+    if (dev < 0 || dev >= device_count()) return false;
+    t_state.device = dev;
+    return true;
+}
+
+int sm_count(int dev) {
+    init_device(dev);
+    return g_devs[dev].sm_count;
+}
+
+DeviceGuard::DeviceGuard(int dev) : prev(-1) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) CWCU_CHECK(cudaSetDevice(dev));
+}
+DeviceGuard::~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) (void)cudaSetDevice(prev);
+}
+
+cudaStream_t thread_stream(int dev) {
+    if (dev < 0 || dev >= device_count()) throw CudaError{cudaErrorInvalidDevice, "no such CUDA device: " + std::to_string(dev)};
+    init_device(dev);
+    if ((int)t_state.streams.size() <= dev) t_state.streams.resize(dev + 1, nullptr);
+    if (!t_state.streams[dev]) {
+        DeviceState &st = g_devs[dev];
+        {
+            std::lock_guard<std::mutex> lk(st.mu);
+            if (!st.idle_streams.empty()) {
+                t_state.streams[dev] = st.idle_streams.back();
+                st.idle_streams.pop_back();
+            }
+        }
+        if (!t_state.streams[dev]) {
+            DeviceGuard g(dev);
+            cudaStream_t s;
+            CWCU_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            t_state.streams[dev] = s;
+        }
+    }
+    return t_state.streams[dev];
+}
+
+// ------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------
+void *dmalloc(size_t bytes, cudaStream_t s) {
+    if (bytes == 0) bytes = 16;
+    void *p = nullptr;
+    CWCU_CHECK(cudaMallocAsync(&p, bytes, s));
+    return p;
+}
+
+void dfree(void *p, cudaStream_t s) noexcept {
+    if (!p) return;
+    cudaError_t e = cudaFreeAsync(p, s);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+}
+
+void *thread_pinned(size_t bytes) {
+    if (bytes < 4096) bytes = 4096;
+    if (t_state.pinned_size < bytes) {
+        if (t_state.pinned) (void)cudaFreeHost(t_state.pinned);
+        t_state.pinned = nullptr;
+        t_state.pinned_size = 0;
+        void *p = nullptr;
+        CWCU_CHECK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        t_state.pinned = p;
+        t_state.pinned_size = bytes;
+    }
+    return t_state.pinned;
+}
+
+bool is_pinned_host(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// ------------------------------------------------------------------------------------------
+// events
+// ------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_event_mu;
+std::vector<cudaEvent_t> g_event_pool;
+} // namespace
+
+cudaEvent_t event_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_event_mu);
+        if (!g_event_pool.empty()) {
+            cudaEvent_t e = g_event_pool.back();
+            g_event_pool.pop_back();
+            return e;
+        }
+    }
+    cudaEvent_t e;
+    CWCU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return e;
+}
+
+void event_release(cudaEvent_t e) noexcept {
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(g_event_mu);
+    g_event_pool.push_back(e);
+}
+
+// ------------------------------------------------------------------------------------------
+// storage
+// ------------------------------------------------------------------------------------------
+Storage::Storage(int dev_, size_t capacity_, cudaStream_t home_) : dev(dev_), capacity(capacity_), home(home_) {
+    DeviceGuard g(dev);
+    d_pts = capacity ? static_cast<cwipc_point *>(dmalloc(capacity * sizeof(cwipc_point), home)) : nullptr;
+    ready = event_acquire();
+}
+
+Storage::~Storage() {
+    // Runs on whichever thread drops the last reference.  Order the free after every reader.
+    try {
+        DeviceGuard g(dev);
+        for (auto &r : readers) {
+            (void)cudaStreamWaitEvent(home, r.second, 0);
+            event_release(r.second);
+        }
+        dfree(d_pts, home);
+        event_release(ready);
+    } catch (...) {
+    }
+}
+
+void Storage::mark_ready() { CWCU_CHECK(cudaEventRecord(ready, home)); }
+
+void Storage::acquire_for_read(cudaStream_t s) {
+    if (s != home) CWCU_CHECK(cudaStreamWaitEvent(s, ready, 0));
+}
+
+void Storage::release_after_read(cudaStream_t s) {
+    if (s == home) return;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &r : readers) {
+        if (r.first == s) {
+            CWCU_CHECK(cudaEventRecord(r.second, s));
+            return;
+        }
+    }
+    cudaEvent_t e = event_acquire();
+    CWCU_CHECK(cudaEventRecord(e, s));
+    readers.emplace_back(s, e);
+}
+
+// ------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ------------------------------------------------------------------------------------------
+std::atomic<uint64_t> g_kernel_launches{0};
+
+namespace {
+std::atomic<bool> g_profile_on{false};
+std::mutex g_profile_mu;
+struct ProfRec {
+    const char *name;
+    cudaEvent_t e0, e1;
+};
+std::vector<ProfRec> g_profile_recs;
+std::map<std::string, std::pair<uint64_t, double>> g_profile_acc; // name -> (launches, ms)
+
+void profile_drain_locked() {
+    for (auto &r : g_profile_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto &acc = g_profile_acc[r.name];
+            acc.first += 1;
+            acc.second += ms;
+        } else {
+            (void)cudaGetLastError();
+        }
+        (void)cudaEventDestroy(r.e0);
+        (void)cudaEventDestroy(r.e1);
+    }
+    g_profile_recs.clear();
+}
+} // namespace
+
+LaunchScope::LaunchScope(const char *name_, cudaStream_t s_) : name(name_), s(s_) {
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_profile_on.load(std::memory_order_relaxed)) {
+        if (cudaEventCreate(&e0) == cudaSuccess) (void)cudaEventRecord(e0, s);
+        else e0 = nullptr;
+    }
+}
+
+LaunchScope::~LaunchScope() {
+    if (!e0) return;
+    cudaEvent_t e1 = nullptr;
+    if (cudaEventCreate(&e1) != cudaSuccess) {
+        (void)cudaEventDestroy(e0);
+        return;
+    }
+    (void)cudaEventRecord(e1, s);
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    g_profile_recs.push_back({name, e0, e1});
+    if (g_profile_recs.size() > 8192) profile_drain_locked();
+}
+
+void check_launch(const char *name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        std::ostringstream os;
+        os << "kernel launch failed: " << name << ": " << cudaGetErrorName(e) << ": " << cudaGetErrorString(e);
+        throw CudaError{e, os.str()};
+    }
+}
+
+void profile_enable(bool on) { g_profile_on.store(on); }
+
+void profile_reset() {
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    profile_drain_locked();
+    g_profile_acc.clear();
+}
+
+std::string profile_report_json() {
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    profile_drain_locked();
+    std::ostringstream os;
+    os << "{";
+    bool first = true;
+    for (auto &kv : g_profile_acc) {
+        if (!first) os << ", ";
+        first = false;
+        os << "\"" << kv.first << "\": {\"launches\": " << kv.second.first << ", \"total_ms\": " << kv.second.second << "}";
+    }
+    os << "}";
+    return os.str();
+}
+
+} // namespace cwcu

@@ -1,0 +1,135 @@
+// runtime.hpp -- device plumbing shared by every translation unit of libcwipc_util_cuda:
+// per-thread streams, stream-ordered device memory, refcounted point storage, launch accounting.
+//
+// Design notes:
+//  * one stream per (host thread, device); a cloud remembers the stream that produced it
+//    ("home") and an event recorded when its contents became valid.  A consumer on another
+//    stream waits on that event; the storage is returned to the pool on its home stream after
+//    waiting for every foreign reader.  No global lock is held while work is queued.
+//  * device memory comes from the device's default cudaMemPool (cudaMallocAsync) with the release
+//    threshold raised, so steady-state frames never reach cudaMalloc.
+//  * there is NO host fallback: every entry point that needs a device fails loudly without one.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cwipc_util_cuda.h"
+
+namespace cwcu {
+
+// ---- logging (logging.cpp); mirrors src/logging.cpp + include/cwipc_util/internal/logging.hpp ----
+void log(cwipc_log_level level, const std::string &module, const std::string &message);
+void log_set_errorbuf(char **errorbuf);
+cwipc_log_level log_get_level();
+
+// ---- errors ----
+struct CudaError {
+    cudaError_t code;
+    std::string what;
+};
+[[noreturn]] void throw_cuda(cudaError_t e, const char *expr, const char *file, int line);
+#define CWCU_CHECK(expr)                                                      \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) ::cwcu::throw_cuda(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// ---- devices and streams ----
+int device_count();                 // 0 when no usable device
+int current_device();               // thread-local selection (default $CWIPC_CUDA_DEVICE or 0)
+bool set_current_device(int dev);
+cudaStream_t thread_stream(int dev); // the calling thread's stream on `dev` (created on first use)
+int sm_count(int dev);
+
+// RAII: make `dev` the CUDA-current device of this thread for the scope.
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev);
+    ~DeviceGuard();
+};
+
+// ---- memory ----
+void *dmalloc(size_t bytes, cudaStream_t s);      // never returns nullptr for bytes>0 (throws)
+void dfree(void *p, cudaStream_t s) noexcept;
+// Small page-locked scratch owned by the calling thread (count readbacks etc.), >= bytes, 16B aligned.
+void *thread_pinned(size_t bytes);
+bool is_pinned_host(const void *p);
+
+// Scratch block freed (stream-ordered) at scope exit.
+struct Scratch {
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    Scratch() = default;
+    Scratch(size_t bytes, cudaStream_t stream) : p(bytes ? dmalloc(bytes, stream) : nullptr), s(stream) {}
+    Scratch(const Scratch &) = delete;
+    Scratch &operator=(const Scratch &) = delete;
+    Scratch(Scratch &&o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
+    Scratch &operator=(Scratch &&o) noexcept {
+        if (this != &o) { release(); p = o.p; s = o.s; o.p = nullptr; }
+        return *this;
+    }
+    ~Scratch() { release(); }
+    void release() noexcept { if (p) { dfree(p, s); p = nullptr; } }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// ---- events ----
+cudaEvent_t event_acquire();             // timing disabled
+void event_release(cudaEvent_t e) noexcept;
+
+// ---- point storage ----
+// `count` valid 16-byte points at d_pts (capacity >= count).  Immutable once `ready` has fired.
+struct Storage {
+    int dev = 0;
+    cwipc_point *d_pts = nullptr;
+    size_t capacity = 0;
+    size_t count = 0;
+    cudaStream_t home = nullptr;
+    cudaEvent_t ready = nullptr;
+    std::mutex mu;
+    std::vector<std::pair<cudaStream_t, cudaEvent_t>> readers; // latest read per foreign stream
+
+    Storage(int dev, size_t capacity, cudaStream_t home);
+    ~Storage();
+    Storage(const Storage &) = delete;
+    Storage &operator=(const Storage &) = delete;
+
+    void mark_ready();                    // record `ready` on home (call after the producing work is queued)
+    void acquire_for_read(cudaStream_t s); // make `s` wait until contents are valid
+    void release_after_read(cudaStream_t s); // note that work queued so far on `s` reads this storage
+};
+using StoragePtr = std::shared_ptr<Storage>;
+
+// ---- launch accounting / profiling ----
+extern std::atomic<uint64_t> g_kernel_launches;
+struct LaunchScope {
+    const char *name;
+    cudaStream_t s;
+    cudaEvent_t e0 = nullptr;
+    LaunchScope(const char *name, cudaStream_t s);
+    ~LaunchScope();
+};
+void check_launch(const char *name);
+
+// launch("kernel_name", stream, [&]{ kernel<<<grid, block, smem, stream>>>(args...); });
+template <class F>
+inline void launch(const char *name, cudaStream_t s, F &&f) {
+    LaunchScope scope(name, s);
+    f();
+    check_launch(name);
+}
+
+void profile_enable(bool on);
+void profile_reset();
+std::string profile_report_json();
+
+inline size_t div_up(size_t a, size_t b) { return (a + b - 1) / b; }
+
+} // namespace cwcu
