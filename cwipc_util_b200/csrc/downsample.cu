@@ -525,8 +525,8 @@ Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_spl
     Scratch box(sizeof(OctreeBox), s);
     const float octree_cellsize = 64 * cellsize;           // ref: src/cwipc_filters.cpp:113-114 (float)
     const double res = (double)octree_cellsize;
-    launch("chunk_bbox_kernel", s, [&] { chunk_bbox_kernel<<<nchunks, BB_THREADS, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>()); });
-    launch("octree_box_kernel", s, [&] {
+    launch("chunk_bbox_kernel", s, 16 * (size_t)n, [&] { chunk_bbox_kernel<<<nchunks, BB_THREADS, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>()); });
+    launch("octree_box_kernel", s, 24 * (size_t)nchunks, [&] {
         octree_box_kernel<<<1, 1024, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, box.as<OctreeBox>());
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
@@ -621,7 +621,7 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
     Scratch keys_a(n * sizeof(uint64_t), s), keys_b(n * sizeof(uint64_t), s);
     Scratch flag(sizeof(uint32_t), s);
     CWCU_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
-    launch("voxel_keygen_kernel", s, [&] { voxel_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in->d_pts, (uint32_t)n, kp, keys_a.as<uint64_t>(), 1, flag.as<uint32_t>()); });
+    launch("voxel_keygen_kernel", s, 24 * (size_t)n, [&] { voxel_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in->d_pts, (uint32_t)n, kp, keys_a.as<uint64_t>(), 1, flag.as<uint32_t>()); });
     uint64_t *sorted = radix_sort_u64(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), n, kp.idxbits, kp.idxbits + plan.keybits, dev, s);
 
     // fixed-point scale: |x| * 2^shift * n < 2^62
@@ -648,7 +648,7 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
     uint32_t *done = ticket + 1, *d_total = ticket + 2;
 
     auto out = std::make_shared<Storage>(dev, n, s);
-    launch("voxel_reduce_kernel", s, [&] {
+    launch("voxel_reduce_kernel", s, 24 * (size_t)n, [&] {
         voxel_reduce_kernel<<<ntiles, VR_THREADS, 0, s>>>(sorted, (uint32_t)n, kp.idxbits, in->d_pts, scale, inv_scale, out->d_pts, ticket,
                                                            reinterpret_cast<uint64_t *>(ab + off_status), reinterpret_cast<TileRecord *>(ab + off_records),
                                                            reinterpret_cast<VoxelAgg *>(ab + off_head), reinterpret_cast<VoxelAgg *>(ab + off_tail), done, ntiles, d_total);
@@ -663,6 +663,7 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
         return result;
     }
     out->count = h[0];
+    profile_add_bytes("voxel_reduce_kernel", 16 * (size_t)h[0]); // voxels written
     out->mark_ready();
     result.out = out;
     return result;
@@ -673,8 +674,8 @@ void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], 
     const uint32_t nchunks = (uint32_t)div_up(n, BB_CHUNK);
     Scratch chunk_bbox((size_t)nchunks * 6 * sizeof(float), s);
     Scratch box(sizeof(OctreeBox), s);
-    launch("chunk_bbox_kernel", s, [&] { chunk_bbox_kernel<<<nchunks, BB_THREADS, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>()); });
-    launch("octree_box_kernel", s, [&] { octree_box_kernel<<<1, 1024, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, box.as<OctreeBox>()); });
+    launch("chunk_bbox_kernel", s, 16 * (size_t)n, [&] { chunk_bbox_kernel<<<nchunks, BB_THREADS, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>()); });
+    launch("octree_box_kernel", s, 24 * (size_t)nchunks, [&] { octree_box_kernel<<<1, 1024, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, box.as<OctreeBox>()); });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
@@ -692,7 +693,7 @@ void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_s
     Scratch keys(n * sizeof(uint64_t), s);
     Scratch flag(sizeof(uint32_t), s);
     CWCU_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
-    launch("voxel_keygen_kernel", s, [&] { voxel_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in->d_pts, (uint32_t)n, plan.kp, keys.as<uint64_t>(), 0, flag.as<uint32_t>()); });
+    launch("voxel_keygen_kernel", s, 24 * (size_t)n, [&] { voxel_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in->d_pts, (uint32_t)n, plan.kp, keys.as<uint64_t>(), 0, flag.as<uint32_t>()); });
     CWCU_CHECK(cudaMemcpyAsync(host_keys, keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
 }

@@ -446,11 +446,11 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
              const uint32_t *d_ncells, float *d_dist, FarEntry *far_list, uint32_t *far_count, int dev, cudaStream_t s) {
     const int kk = k + 1;
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(n, (size_t)32), (size_t)sm_count(dev) * 16));
-    launch("knn_cell_kernel", s, [&] {
+    launch("knn_cell_kernel", s, 28 * (size_t)n, [&] {
         knn_cell_kernel<KCAP><<<grid, 128, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, cell_start, cell_code, d_ncells, d_dist, far_list, far_count);
     });
     for (int level = 1; level <= gp.top_level; level++) {
-        launch("knn_far_kernel", s, [&] {
+        launch("knn_far_kernel", s, (size_t)0, [&] {
             knn_far_kernel<KCAP><<<(unsigned)sm_count(dev) * 8, 128, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, (uint32_t)level, cell_start, cell_code, d_ncells, d_dist,
                                                                             far_list, far_count);
         });
@@ -474,11 +474,11 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     const int keybits = 3 * axis_bits;
 
     Scratch keys_a(n * sizeof(uint64_t), s), keys_b(n * sizeof(uint64_t), s);
-    launch("knn_keygen_kernel", s, [&] { knn_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in, (uint32_t)n, gp, keys_a.as<uint64_t>()); });
+    launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] { knn_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in, (uint32_t)n, gp, keys_a.as<uint64_t>()); });
     const uint64_t *sorted = radix_sort_u64(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), n, gp.idxbits, gp.idxbits + keybits, dev, s);
 
     Scratch spts(n * sizeof(cwipc_point), s);
-    launch("knn_gather_kernel", s, [&] { knn_gather_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, in, spts.as<cwipc_point>()); });
+    launch("knn_gather_kernel", s, 40 * (size_t)n, [&] { knn_gather_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, in, spts.as<cwipc_point>()); });
 
     // occupied cells
     const size_t ntiles = div_up(n, CH_TILE);
@@ -490,7 +490,7 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     uint32_t *ticket = aux.as<uint32_t>();
     uint32_t *d_ncells = ticket + 1, *far_count = ticket + 2;
     uint64_t *status = reinterpret_cast<uint64_t *>(ticket + 4);
-    launch("cell_heads_kernel", s, [&] {
+    launch("cell_heads_kernel", s, 8 * (size_t)n, [&] {
         cell_heads_kernel<<<(unsigned)ntiles, CH_THREADS, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, cell_start.as<uint32_t>(), cell_code.as<uint64_t>(), ticket, status, d_ncells);
     });
 
@@ -520,7 +520,7 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
     knn_mean_distances(in, n, k, hint_spacing, dist.as<float>(), dev, s);
 
     Scratch partial(2 * ST_BLOCKS * sizeof(double), s);
-    launch("stats_kernel", s, [&] { stats_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>()); });
+    launch("stats_kernel", s, 4 * (size_t)n, [&] { stats_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>()); });
     double *h = static_cast<double *>(thread_pinned(2 * ST_BLOCKS * sizeof(double)));
     CWCU_CHECK(cudaMemcpyAsync(h, partial.p, 2 * ST_BLOCKS * sizeof(double), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *
 }
 
 template <class Pred>
-size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred, cudaStream_t s) {
+size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred, cudaStream_t s, size_t pred_bytes = 16) {
     if (n == 0) return 0;
     const size_t ntiles = div_up(n, CP_TILE);
     // [ticket u32 | total u32 | status u64 * ntiles]
@@ -111,12 +111,13 @@ size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred,
     uint32_t *ticket = scratch.as<uint32_t>();
     uint32_t *d_total = ticket + 1;
     uint64_t *status = reinterpret_cast<uint64_t *>(ticket + 2);
-    launch("compact_kernel", s, [&] {
+    launch("compact_kernel", s, pred_bytes * (size_t)n, [&] {
         compact_kernel<Pred><<<(unsigned)ntiles, CP_THREADS, 0, s>>>(in, (uint32_t)n, out, pred, ticket, status, d_total);
     });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
+    profile_add_bytes("compact_kernel", 16 * (size_t)*h); // survivors written
     return *h;
 }
 
@@ -195,7 +196,7 @@ size_t compact_points(const cwipc_point *in, size_t n, cwipc_point *out, const P
     case PredKind::CropBox:
         return run_compact(in, n, out, CropPred{pred.box[0], pred.box[1], pred.box[2], pred.box[3], pred.box[4], pred.box[5]}, s);
     case PredKind::DistanceAtMost:
-        return run_compact(in, n, out, DistPred{pred.dist, pred.threshold}, s);
+        return run_compact(in, n, out, DistPred{pred.dist, pred.threshold}, s, 20);
     }
     return 0;
 }
@@ -211,13 +212,13 @@ void tilemap_points(const cwipc_point *in, size_t n, cwipc_point *out, const uin
     TileMap tm;
     memcpy(tm.m, map, 256);
     const unsigned grid = grid_for(n, 256, device_of_stream_guard(), 8);
-    launch("tilemap_kernel", s, [&] { tilemap_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, out, tm); });
+    launch("tilemap_kernel", s, 32 * (size_t)n, [&] { tilemap_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, out, tm); });
 }
 
 void colormap_points(const cwipc_point *in, size_t n, cwipc_point *out, uint32_t clearBits, uint32_t setBits, cudaStream_t s) {
     if (n == 0) return;
     const unsigned grid = grid_for(n, 256, device_of_stream_guard(), 8);
-    launch("colormap_kernel", s, [&] { colormap_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, out, clearBits, setBits); });
+    launch("colormap_kernel", s, 32 * (size_t)n, [&] { colormap_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, out, clearBits, setBits); });
 }
 
 float min_distance_to_first(const cwipc_point *in, size_t n, cudaStream_t s) {
@@ -225,7 +226,7 @@ float min_distance_to_first(const cwipc_point *in, size_t n, cudaStream_t s) {
     Scratch scratch(sizeof(uint32_t), s);
     CWCU_CHECK(cudaMemsetAsync(scratch.p, 0xff, sizeof(uint32_t), s)); // 0xffffffff > any finite non-negative float pattern
     const unsigned grid = grid_for(n, 256, device_of_stream_guard(), 8);
-    launch("min_dist2_kernel", s, [&] { min_dist2_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, scratch.as<uint32_t>()); });
+    launch("min_dist2_kernel", s, 16 * (size_t)n, [&] { min_dist2_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, scratch.as<uint32_t>()); });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, scratch.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
@@ -241,7 +242,7 @@ std::vector<int> tiles_in_first_appearance_order(const cwipc_point *in, size_t n
     Scratch scratch(256 * sizeof(uint32_t), s);
     CWCU_CHECK(cudaMemsetAsync(scratch.p, 0xff, 256 * sizeof(uint32_t), s));
     const unsigned grid = grid_for(n, 256, device_of_stream_guard(), 4);
-    launch("first_tile_kernel", s, [&] { first_tile_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, scratch.as<uint32_t>()); });
+    launch("first_tile_kernel", s, 16 * (size_t)n, [&] { first_tile_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, scratch.as<uint32_t>()); });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(256 * sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, scratch.p, 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));

@@ -213,14 +213,14 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
     uint32_t *status = tickets + 8;
 
     const unsigned hist_grid = (unsigned)std::max<size_t>(1, std::min(div_up(n, (size_t)RS_THREADS * 8), (size_t)sm_count(dev) * 8));
-    launch("radix_hist_kernel", s, [&] { radix_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(a, (uint32_t)n, begin_bit, end_bit, npasses, hist); });
-    launch("radix_scan_kernel", s, [&] { radix_scan_kernel<<<npasses, RS_BINS, 0, s>>>(hist, binbase); });
+    launch("radix_hist_kernel", s, 8 * (size_t)n, [&] { radix_hist_kernel<<<hist_grid, RS_THREADS, 0, s>>>(a, (uint32_t)n, begin_bit, end_bit, npasses, hist); });
+    launch("radix_scan_kernel", s, (size_t)2048 * npasses, [&] { radix_scan_kernel<<<npasses, RS_BINS, 0, s>>>(hist, binbase); });
 
     uint64_t *src = a, *dst = b;
     for (int p = 0; p < npasses; p++) {
         const int shift = begin_bit + 8 * p;
         const int bits = std::min(8, end_bit - shift);
-        launch("radix_onesweep_kernel", s, [&] {
+        launch("radix_onesweep_kernel", s, 16 * (size_t)n, [&] {
             radix_onesweep_kernel<<<(unsigned)ntiles, RS_THREADS, 0, s>>>(src, dst, (uint32_t)n, shift, bits, binbase + (size_t)p * RS_BINS, tickets + p,
                                                                            status + (size_t)p * ntiles * RS_BINS);
         });

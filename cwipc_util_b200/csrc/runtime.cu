@@ -261,17 +261,24 @@ std::mutex g_profile_mu;
 struct ProfRec {
     const char *name;
     cudaEvent_t e0, e1;
+    size_t bytes;
+};
+struct ProfAcc {
+    uint64_t launches = 0;
+    double ms = 0.0;
+    double bytes = 0.0;
 };
 std::vector<ProfRec> g_profile_recs;
-std::map<std::string, std::pair<uint64_t, double>> g_profile_acc; // name -> (launches, ms)
+std::map<std::string, ProfAcc> g_profile_acc;
 
 void profile_drain_locked() {
     for (auto &r : g_profile_recs) {
         float ms = 0.f;
         if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
             auto &acc = g_profile_acc[r.name];
-            acc.first += 1;
-            acc.second += ms;
+            acc.launches += 1;
+            acc.ms += ms;
+            acc.bytes += (double)r.bytes;
         } else {
             (void)cudaGetLastError();
         }
@@ -282,7 +289,7 @@ void profile_drain_locked() {
 }
 } // namespace
 
-LaunchScope::LaunchScope(const char *name_, cudaStream_t s_) : name(name_), s(s_) {
+LaunchScope::LaunchScope(const char *name_, cudaStream_t s_, size_t bytes_) : name(name_), s(s_), bytes(bytes_) {
     g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
     if (g_profile_on.load(std::memory_order_relaxed)) {
         if (cudaEventCreate(&e0) == cudaSuccess) (void)cudaEventRecord(e0, s);
@@ -299,7 +306,7 @@ LaunchScope::~LaunchScope() {
     }
     (void)cudaEventRecord(e1, s);
     std::lock_guard<std::mutex> lk(g_profile_mu);
-    g_profile_recs.push_back({name, e0, e1});
+    g_profile_recs.push_back({name, e0, e1, bytes});
     if (g_profile_recs.size() > 8192) profile_drain_locked();
 }
 
@@ -313,6 +320,12 @@ void check_launch(const char *name) {
 }
 
 void profile_enable(bool on) { g_profile_on.store(on); }
+
+void profile_add_bytes(const char *name, size_t bytes) {
+    if (!g_profile_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    g_profile_acc[name].bytes += (double)bytes;
+}
 
 void profile_reset() {
     std::lock_guard<std::mutex> lk(g_profile_mu);
@@ -329,7 +342,7 @@ std::string profile_report_json() {
     for (auto &kv : g_profile_acc) {
         if (!first) os << ", ";
         first = false;
-        os << "\"" << kv.first << "\": {\"launches\": " << kv.second.first << ", \"total_ms\": " << kv.second.second << "}";
+        os << "\"" << kv.first << "\": {\"launches\": " << kv.second.launches << ", \"total_ms\": " << kv.second.ms << ", \"bytes\": " << (uint64_t)kv.second.bytes << "}";
     }
     os << "}";
     return os.str();

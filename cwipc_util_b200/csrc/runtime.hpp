@@ -112,19 +112,23 @@ extern std::atomic<uint64_t> g_kernel_launches;
 struct LaunchScope {
     const char *name;
     cudaStream_t s;
+    size_t bytes;
     cudaEvent_t e0 = nullptr;
-    LaunchScope(const char *name, cudaStream_t s);
+    LaunchScope(const char *name, cudaStream_t s, size_t algorithmic_bytes);
     ~LaunchScope();
 };
 void check_launch(const char *name);
 
-// launch("kernel_name", stream, [&]{ kernel<<<grid, block, smem, stream>>>(args...); });
+// launch("kernel_name", stream, algorithmic_bytes, [&]{ kernel<<<grid, block, smem, stream>>>(args...); });
+// algorithmic_bytes: the bytes this launch must move at minimum; only used by the profile.
 template <class F>
-inline void launch(const char *name, cudaStream_t s, F &&f) {
-    LaunchScope scope(name, s);
+inline void launch(const char *name, cudaStream_t s, size_t algorithmic_bytes, F &&f) {
+    LaunchScope scope(name, s, algorithmic_bytes);
     f();
     check_launch(name);
 }
+// bytes that are only known after a readback (e.g. survivors written by a compaction)
+void profile_add_bytes(const char *name, size_t bytes);
 
 void profile_enable(bool on);
 void profile_reset();
