@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the cwipc filter hot path on B200.
+
+Metric (BASELINE.json): Mpoints/s for downsample + remove_outliers at 1/2/4/8 B200; % of HBM GB/s peak.
+
+Workload (BASELINE.json configs[4], the config the metric is quoted on): a sequence of 1M-point
+(1000 x 1000) 4-camera synthetic frames, per frame  cwipc_downsample(0.01) -> cwipc_remove_outliers(30, 1.0,
+perTile=False), frame-sharded over the GPUs with no collective on the data path.  240 frames at 8 GPUs =
+30 frames per GPU per step; scaling is WEAK (30 frames per GPU per step at every N).  A step is one pass
+over a rank's 30 frames.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm (CUDA library through its C ABI)
+    python bench.py --impl reference --gpus 1 ...             # the reference's CPU path (oracle port, all host cores)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`value`   : device-resident inputs, CUDA-event timed (max over worker streams and over ranks).
+`e2e`     : same frames from page-locked HOST buffers through cwipc_from_points (H2D inside the timed
+            region) and the result read back with cwipc_pointcloud_copy_uncompressed (D2H inside).
+`roofline`: dominant kernel of the step (largest total device time in a profiled pass of the same step):
+            algorithmic bytes of its launches / their CUDA-event duration, against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle (a single-threaded port of the reference path) timed on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+POINTS_PER_FRAME = 1000 * 1000
+VOXEL = 0.01
+K, STDDEV = 30, 1.0
+FRAMES_PER_GPU = 30          # 240 frames / 8 GPUs
+WORKERS = 4                  # host threads (one CUDA stream each) feeding one GPU
+HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------
+def make_frames(first, count, stride):
+    """Frames first, first+stride, ...: same geometry, per-frame jitter/outliers seeded by the frame index."""
+    from cwipc_util_b200 import synthetic
+    base = synthetic.simulate_cameras(synthetic.synthetic_cloud(POINTS_PER_FRAME), 4)
+    frames = []
+    for j in range(count):
+        seed = first + j * stride
+        frames.append(synthetic.add_outliers(synthetic.add_noise(base, 0.002, seed), 0.005, seed))
+    return frames
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self._halt.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.01)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+class Worker(threading.Thread):
+    """One host thread = one CUDA stream.  Processes its share of the rank's frames every step."""
+
+    def __init__(self, wid, nworkers, dev, cw, lib, barrier, state):
+        super().__init__(daemon=True)
+        self.wid, self.nworkers, self.dev, self.cw, self.lib = wid, nworkers, dev, cw, lib
+        self.barrier, self.state = barrier, state
+        self.error = None
+        self.timers = []          # one timer per step
+        self.out_points = 0
+        self.mid_points = 0
+        self.d2h_bytes = 0
+
+    def frame_chain(self, pc):
+        d = self.cw.cwipc_downsample(pc, VOXEL)
+        o = self.cw.cwipc_remove_outliers(d, K, STDDEV, False)
+        self.mid_points += d.count()
+        d.free()
+        return o
+
+    def run(self):
+        try:
+            cw, lib, st = self.cw, self.lib, self.state
+            cw.cuda_set_device(self.dev)
+            mine = list(range(self.wid, len(st["frames"]), self.nworkers))
+            while True:
+                self.barrier.wait()                      # step start (or shutdown)
+                if st["stop"]:
+                    return
+                mode = st["mode"]
+                timer = lib.cwipc_cuda_timer_create()
+                self.timers.append(timer)
+                self.out_points = 0
+                self.mid_points = 0
+                self.d2h_bytes = 0
+                lib.cwipc_cuda_timer_start(timer)
+                for f in mine:
+                    if mode == "resident":
+                        o = self.frame_chain(st["device_frames"][f])
+                        self.out_points += o.count()
+                        o.free()
+                    else:  # e2e: pinned host -> device -> filters -> pinned host
+                        err = ctypes.c_char_p()
+                        p = lib.cwipc_from_points(st["host_ptrs"][f], POINTS_PER_FRAME * 16, POINTS_PER_FRAME, f, ctypes.byref(err), cw.CWIPC_API_VERSION)
+                        if not p:
+                            raise RuntimeError(f"cwipc_from_points failed: {err.value}")
+                        pc = cw.cwipc_pointcloud_wrapper(p)
+                        pc._set_cellsize(st["cellsize"])
+                        o = self.frame_chain(pc)
+                        nbytes = o.get_uncompressed_size()
+                        got = lib.cwipc_pointcloud_copy_uncompressed(o.as_cwipc_p(), st["host_out"][self.wid], nbytes)
+                        if got < 0:
+                            raise RuntimeError("copy_uncompressed failed")
+                        self.out_points += got
+                        self.d2h_bytes += nbytes
+                        o.free()
+                        pc.free()
+                lib.cwipc_cuda_timer_stop(timer)
+                cw.cuda_synchronize()
+                self.barrier.wait()                      # step end
+        except Exception as e:  # pragma: no cover
+            self.error = e
+            try:
+                self.barrier.abort()
+            except Exception:
+                pass
+
+
+def run_steps(workers, barrier, state, lib, mode, nsteps):
+    """Run nsteps steps in `mode`; return per-step device times in ms (max over worker-stream pairs)."""
+    state["mode"] = mode
+    times = []
+    for _ in range(nsteps):
+        barrier.wait()
+        barrier.wait()
+        for w in workers:
+            if w.error:
+                raise w.error
+        ts = [w.timers[-1] for w in workers]
+        ms = max(lib.cwipc_cuda_timer_span_ms(a, b) for a in ts for b in ts)
+        times.append(ms)
+    for w in workers:
+        for t in w.timers:
+            lib.cwipc_cuda_timer_destroy(t)
+        w.timers = []
+    return times
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+        return world, rank, local, dist, torch
+    return world, rank, local, None, None
+
+
+def dist_barrier(dist, torch):
+    if dist is not None:
+        t = torch.zeros(1, device="cuda")
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+
+def dist_reduce(dist, torch, value, op):
+    if dist is None:
+        return value
+    t = torch.tensor([float(value)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+    return float(t.item())
+
+
+def measured_hbm_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline_sample(frames, nframes):
+    """The oracle (single-threaded port of the reference path) on a bounded sample of the same frames."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle
+    from cwipc_util_b200 import synthetic
+    cellsize = synthetic.cellsize_of(POINTS_PER_FRAME)
+    oracle.load()
+    t0 = time.perf_counter()
+    for f in range(nframes):
+        pts = frames[f % len(frames)]
+        ds, cs, _, _ = oracle.downsample(pts, VOXEL, cellsize)
+        oracle.remove_outliers(ds, K, STDDEV, False)
+    dt = time.perf_counter() - t0
+    return nframes * POINTS_PER_FRAME / dt / 1e6, dt
+
+
+def run_ours(args):
+    world, rank, local, dist, torch = dist_setup(args)
+    import cwipc_util_b200 as cw
+    from cwipc_util_b200 import synthetic
+    lib = cw.util.cwipc_util_dll_load()
+    if cw.cuda_device_count() <= 0:
+        raise SystemExit("bench.py: libcwipc_util_cuda sees no CUDA device (there is no CPU fallback)")
+    dev = local if cw.cuda_device_count() > local else 0
+    cw.cuda_set_device(dev)
+    nframes = args.frames_per_gpu
+    cellsize = synthetic.cellsize_of(POINTS_PER_FRAME)
+
+    t0 = time.perf_counter()
+    frames = make_frames(rank, nframes, world)          # frame f of the sequence goes to GPU f mod N
+    log(f"[rank {rank}] generated {nframes} frames in {time.perf_counter() - t0:.1f}s")
+
+    # device-resident copies (for `value`) and page-locked host copies (for `e2e`)
+    device_frames, host_ptrs = [], []
+    for f, pts in enumerate(frames):
+        pc = cw.cwipc_from_numpy_array(pts, f)
+        pc._set_cellsize(cellsize)
+        device_frames.append(pc)
+        hp = lib.cwipc_cuda_host_alloc(POINTS_PER_FRAME * 16)
+        ctypes.memmove(hp, pts.ctypes.data, POINTS_PER_FRAME * 16)
+        host_ptrs.append(hp)
+    nworkers = args.workers
+    host_out = [lib.cwipc_cuda_host_alloc(POINTS_PER_FRAME * 16) for _ in range(nworkers)]
+    state = {"frames": frames, "device_frames": device_frames, "host_ptrs": host_ptrs, "host_out": host_out, "cellsize": cellsize, "stop": False, "mode": "resident"}
+    barrier = threading.Barrier(nworkers + 1)
+    workers = [Worker(w, nworkers, dev, cw, lib, barrier, state) for w in range(nworkers)]
+    for w in workers:
+        w.start()
+
+    # ---- warm-up (both paths), then the timed regions ----
+    run_steps(workers, barrier, state, lib, "resident", args.warmup)
+    run_steps(workers, barrier, state, lib, "e2e", max(1, args.warmup // 2))
+    cw.cuda_synchronize()
+    dist_barrier(dist, torch)
+
+    sampler = ClockSampler(dev)
+    sampler.start()
+    launches0 = cw.cuda_kernel_launches()
+    times = run_steps(workers, barrier, state, lib, "resident", args.steps)
+    launches = cw.cuda_kernel_launches() - launches0
+    out_points = sum(w.out_points for w in workers)
+    mid_points = sum(w.mid_points for w in workers)
+    dist_barrier(dist, torch)
+    e2e_times = run_steps(workers, barrier, state, lib, "e2e", args.steps)
+    d2h_bytes = sum(w.d2h_bytes for w in workers)
+    clocks = sampler.stop()
+    dist_barrier(dist, torch)
+
+    # ---- roofline: a profiled pass of the same step (events around every kernel) ----
+    prof = {}
+    if rank == 0:
+        lib.cwipc_cuda_profile_reset()
+        lib.cwipc_cuda_profile_enable(1)
+        run_steps(workers, barrier, state, lib, "resident", 1)
+        lib.cwipc_cuda_profile_enable(0)
+        need = lib.cwipc_cuda_profile_report(None, 0)
+        buf = ctypes.create_string_buffer(need)
+        lib.cwipc_cuda_profile_report(buf, need)
+        prof = json.loads(buf.value.decode())
+    else:
+        run_steps(workers, barrier, state, lib, "resident", 1)
+
+    state["stop"] = True
+    barrier.wait()
+
+    # ---- aggregate over ranks: time = max over ranks, work = sum ----
+    total_ms = dist_reduce(dist, torch, sum(times), "MAX")
+    total_e2e_ms = dist_reduce(dist, torch, sum(e2e_times), "MAX")
+    launches_all = dist_reduce(dist, torch, launches, "SUM")
+    d2h_all = dist_reduce(dist, torch, d2h_bytes, "SUM")
+    points_per_step = nframes * POINTS_PER_FRAME * world
+    value = points_per_step * args.steps / (total_ms / 1e3) / 1e6
+    e2e_value = points_per_step * args.steps / (total_e2e_ms / 1e3) / 1e6
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_hbm_peak()
+    roofline = None
+    if prof:
+        name, rec = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
+        achieved = rec["bytes"] / (rec["total_ms"] / 1e3) / 1e9 if rec["total_ms"] > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(name)
+        except Exception:
+            pass
+        step_kernel_ms = sum(r["total_ms"] for r in prof.values())
+        roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": traffic, "peak_source": peak_src, "launches": rec["launches"], "avg_launch_us": round(rec["total_ms"] * 1e3 / max(1, rec["launches"]), 2),
+                    "algorithmic_bytes_per_launch": int(rec["bytes"] / max(1, rec["launches"])), "share_of_step_kernel_time": round(rec["total_ms"] / step_kernel_ms, 3),
+                    "kernels": {k: {"launches": v["launches"], "ms": round(v["total_ms"], 3), "GBps": round(v["bytes"] / max(v["total_ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}}
+        # whole-op roofline on compulsory bytes: 16 B in + 16 B out per stage
+        # downsample: 16 N in + 16 V out; remove_outliers: 16 V in + 16 M out   (per rank and step)
+        compulsory = 16.0 * (nframes * POINTS_PER_FRAME + 2 * mid_points + out_points)
+        roofline["op_compulsory_GBps_per_gpu"] = round(compulsory / (sum(times) / args.steps / 1e3) / 1e9, 1)
+        roofline["op_compulsory_frac"] = round(roofline["op_compulsory_GBps_per_gpu"] / peak, 4)
+
+    cpu_mpts, cpu_dt = cpu_baseline_sample(frames, args.cpu_frames)
+    line = {
+        "metric": "Mpoints/s for downsample+remove_outliers at 1/2/4/8 B200; % of HBM GB/s peak",
+        "value": round(value, 1), "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 keys/distances, int64 fixed-point sums, f64 statistics", "data": "synthetic",
+        "config": {"workload": "configs[4]: 1M-point 4-camera synthetic frames, per frame cwipc_downsample(0.01) -> cwipc_remove_outliers(30,1.0,perTile=False); "
+                               f"{nframes} frames per GPU per step, frame-sharded, no collective", "points_per_frame": POINTS_PER_FRAME, "frames_per_gpu_per_step": nframes,
+                   "host_threads_per_gpu": nworkers, "l2": f"inputs larger than L2 ({nframes} x 16 MB per GPU per step, each frame touched once per step)",
+                   "parallelism": f"frames x{world}"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "Mpoints/s", "h2d_bytes_per_step": points_per_step * 16, "d2h_bytes_per_step": int(d2h_all / max(1, args.steps)),
+                "ms_per_step": round(total_e2e_ms / args.steps, 3)},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": {"value": round(cpu_mpts, 3), "unit": "Mpoints/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.cpu_frames} of the same frames through oracle/cwipc_oracle.c (downsample 0.01 + remove_outliers 30/1.0), {cpu_dt:.1f}s, single thread"},
+        "out_points_per_step": int(out_points),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (oracle port: the reference itself needs PCL and cannot be built here)
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle
+    from cwipc_util_b200 import synthetic
+    oracle.load()
+    cores = os.cpu_count() or 1
+    nthreads = max(1, cores)
+    per_step = nthreads  # one frame per host thread per step: a bounded sample of the 30*N-frame step
+    frames = make_frames(0, min(per_step, 8), 1)
+    cellsize = synthetic.cellsize_of(POINTS_PER_FRAME)
+
+    def one(i):
+        pts = frames[i % len(frames)]
+        ds, cs, _, _ = oracle.downsample(pts, VOXEL, cellsize)
+        oracle.remove_outliers(ds, K, STDDEV, False)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(nthreads) as ex:
+        for _ in range(args.warmup):
+            list(ex.map(one, range(per_step)))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            list(ex.map(one, range(per_step)))   # ctypes releases the GIL: frames run on all cores
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps * POINTS_PER_FRAME / dt / 1e6
+    line = {
+        "impl": "reference",
+        "metric": "Mpoints/s for downsample+remove_outliers at 1/2/4/8 B200; % of HBM GB/s peak",
+        "value": round(value, 3), "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32/f64 (CPU)", "data": "synthetic",
+        "config": {"workload": "configs[4]: 1M-point 4-camera synthetic frames, per frame cwipc_downsample(0.01) -> cwipc_remove_outliers(30,1.0,perTile=False)",
+                   "points_per_frame": POINTS_PER_FRAME, "frames_per_step": per_step, "parallelism": f"{nthreads} host threads, one frame each"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mpoints/s", "cores": nthreads, "kind": "port",
+                         "sample": f"{per_step} frames per step (one per host thread) through oracle/cwipc_oracle.c; the reference itself needs PCL and cannot be built here"},
+        "e2e": {"value": round(value, 3), "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--workers", type=int, default=WORKERS)
+    ap.add_argument("--cpu-frames", type=int, default=24)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
