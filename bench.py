@@ -39,7 +39,7 @@ POINTS_PER_FRAME = 1000 * 1000
 VOXEL = 0.01
 K, STDDEV = 30, 1.0
 FRAMES_PER_GPU = 30          # 240 frames / 8 GPUs
-WORKERS = 4                  # host threads (one CUDA stream each) feeding one GPU
+WORKERS = 8                  # host threads (one CUDA stream each) feeding one GPU
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -72,6 +72,8 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self.armed = threading.Event()      # samples are kept only while the timed region runs
+        self.ready = threading.Event()      # NVML initialised (it stalls CUDA calls while it loads)
 
     def run(self):
         try:
@@ -85,7 +87,12 @@ class ClockSampler(threading.Thread):
                 getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             }
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.ready.set()
             while not self._halt.is_set():
+                if not self.armed.is_set():
+                    time.sleep(0.005)
+                    continue
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 try:
                     mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -97,6 +104,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.01)
         except Exception as e:  # pragma: no cover
             self.reasons.add(f"sampler_error:{type(e).__name__}")
+            self.ready.set()
 
     def stop(self):
         self._halt.set()
@@ -283,13 +291,15 @@ def run_ours(args):
         w.start()
 
     # ---- warm-up (both paths), then the timed regions ----
+    sampler = ClockSampler(dev)
+    sampler.start()
+    sampler.ready.wait(timeout=30)
     run_steps(workers, barrier, state, lib, "resident", args.warmup)
     run_steps(workers, barrier, state, lib, "e2e", max(1, args.warmup // 2))
     cw.cuda_synchronize()
     dist_barrier(dist, torch)
 
-    sampler = ClockSampler(dev)
-    sampler.start()
+    sampler.armed.set()
     launches0 = cw.cuda_kernel_launches()
     times = run_steps(workers, barrier, state, lib, "resident", args.steps)
     launches = cw.cuda_kernel_launches() - launches0
@@ -298,6 +308,7 @@ def run_ours(args):
     dist_barrier(dist, torch)
     e2e_times = run_steps(workers, barrier, state, lib, "e2e", args.steps)
     d2h_bytes = sum(w.d2h_bytes for w in workers)
+    sampler.armed.clear()
     clocks = sampler.stop()
     dist_barrier(dist, torch)
 
@@ -368,6 +379,7 @@ def run_ours(args):
         "cpu_baseline": {"value": round(cpu_mpts, 3), "unit": "Mpoints/s", "cores": 1, "kind": "port",
                          "sample": f"{args.cpu_frames} of the same frames through oracle/cwipc_oracle.c (downsample 0.01 + remove_outliers 30/1.0), {cpu_dt:.1f}s, single thread"},
         "out_points_per_step": int(out_points),
+        "step_ms": [round(t, 3) for t in times], "e2e_step_ms": [round(t, 3) for t in e2e_times],
     }
     print(json.dumps(line), flush=True)
 

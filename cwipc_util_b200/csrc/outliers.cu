@@ -6,25 +6,28 @@
 //   points (itself included); d_i = (float)( sum_{j=1..k} sqrt((double)d2_j) / k );
 //   mean/variance of d in double (squares taken in float); keep iff !(d_i > mean + mul*stddev).
 //
-// The kd-tree is replaced by a uniform grid in Morton order:
+// The kd-tree is replaced by a uniform grid in Morton order with a dense table pyramid:
 //   knn_keygen_kernel   16 B read + 8 B   key = [Morton(cell) | point index]
 //   radix_sort_u64      P x (8+8) B       (shared with downsample)
-//   knn_gather_kernel   8+16 B read, 16 B points re-laid out in cell order (each cell and every aligned
-//                                         2^l-cube of cells is one contiguous range)
-//   cell_heads_kernel   8 B read          list of occupied cells (decoupled look-back compaction)
-//   knn_cell_kernel     one warp per occupied cell, one lane per query: exact top-(k+1) over the 27
-//                       neighbouring cells, kept as a sorted register array (min/max insertion network).
-//                       A query is final when its (k+1)-th distance is within the distance to the border
-//                       of the 3x3x3 block; otherwise it is queued for a coarser level.
-//   knn_far_kernel      levels 1..L: one warp per queued query, lanes stride over the candidates of the
-//                       27 level-l cells that intersect the known bound, per-lane lists merged by warp
-//                       min-reduction.  The top level spans the whole cloud, so every query terminates.
+//   knn_gather_kernel   8+16 B read, 16 B points re-laid out in cell order: every cell, and every aligned
+//                                         2^l-cube of cells, is one contiguous range of the array
+//   cell_table_kernel   8 B read          dense (begin,end) table of every level, scattered from the
+//                                         positions where the Morton prefix changes
+//   knn_tile_kernel     one warp per 32 consecutive queries, one lane per query.  Candidates = the cells
+//                       within Rc cell pitches of the queries' bounding box, streamed into shared memory
+//                       by TMA bulk copies (one per cell range, double buffered); per lane an adaptive
+//                       threshold + bitonic merge keeps the k+1 smallest distances in sorted registers.
+//                       A query is final when its (k+1)-th distance is within Rc pitches; the rest is queued.
+//   knn_far_kernel      one warp per queued query: depth-first search of the table pyramid (an implicit
+//                       octree), nearest child first, pruned by the running (k+1)-th best.
 //   stats_kernel        sum d, sum (float)(d*d) in double, fixed two-level order (deterministic)
 //   compact_kernel      keep mask + stable compaction (pointops.cu)
-// Exactness never depends on the grid pitch; the pitch only moves work between the levels.
+// Exactness never depends on the grid pitch; the pitch only moves work between the two passes.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "device_utils.cuh"
 #include "kernels.hpp"
@@ -34,14 +37,25 @@ namespace cwcu {
 
 namespace {
 
+constexpr int KG_MAX_LEVELS = 14; // levels 0..13 (at most 13 bits per axis)
+
 struct GridParams {
     float gmin[3];
     float inv_h;   // 1 / cell pitch
     float h;       // cell pitch
-    int gdim[3];   // cells per axis
+    float rc;      // cover radius of the main pass, in cell pitches (<= 1.5)
+    int gdim[3];   // cells per axis at level 0
     int idxbits;
     int top_level; // level at which the whole grid is one cell
+    uint32_t table_off[KG_MAX_LEVELS]; // first entry of each level's table (entries are uint2)
 };
+
+__host__ __device__ __forceinline__ int level_dim(int gdim, int level) { return ((gdim - 1) >> level) + 1; }
+
+__device__ __forceinline__ uint32_t table_index(const GridParams &gp, int level, uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t dx = (uint32_t)level_dim(gp.gdim[0], level), dy = (uint32_t)level_dim(gp.gdim[1], level);
+    return gp.table_off[level] + (z * dy + y) * dx + x;
+}
 
 __device__ __forceinline__ uint64_t spread3(uint32_t v) { // bit i -> bit 3i, v < 2^21
     uint64_t x = v & 0x1fffffu;
@@ -89,283 +103,444 @@ __global__ void __launch_bounds__(256) knn_gather_kernel(const uint64_t *__restr
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) st_point(spts, j, ld_point(pts, (size_t)(sorted[j] & idxmask)));
 }
 
-// ---- occupied cells: positions where the Morton code changes ---------------------------------
-constexpr int CH_THREADS = 256;
-constexpr int CH_ITEMS = 8;
-constexpr int CH_TILE = CH_THREADS * CH_ITEMS;
-
-__global__ void __launch_bounds__(CH_THREADS) cell_heads_kernel(const uint64_t *__restrict__ sorted, uint32_t n, int idxbits, uint32_t *__restrict__ cell_start,
-                                                                 uint64_t *__restrict__ cell_code, uint32_t *__restrict__ ticket, uint64_t *__restrict__ status,
-                                                                 uint32_t *__restrict__ d_ncells) {
-    __shared__ int s_tile;
-    __shared__ uint32_t s_warp_total[CH_THREADS / 32];
-    __shared__ uint32_t s_tile_excl;
-    if (threadIdx.x == 0) s_tile = take_ticket(ticket);
-    __syncthreads();
-    const int tile = s_tile;
-    const uint32_t tile_base = (uint32_t)tile * CH_TILE;
-    if (tile_base >= n) return;
-    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t warp_base = tile_base + warp * (32 * CH_ITEMS);
-    const unsigned lt = lanemask_lt();
-    uint32_t rank[CH_ITEMS];
-    uint64_t code[CH_ITEMS];
-    unsigned headbits = 0;
-    uint32_t running = 0;
-#pragma unroll
-    for (int i = 0; i < CH_ITEMS; i++) {
-        const uint32_t e = warp_base + i * 32 + lane;
-        bool head = false;
-        if (e < n) {
-            code[i] = sorted[e] >> idxbits;
-            head = (e == 0) || ((sorted[e - 1] >> idxbits) != code[i]);
+// ---- table pyramid: (begin, end) of every node of every level ----------------------------------------
+// Position i starts a new level-l node iff the Morton codes of i-1 and i differ above bit 3l.  The
+// thread at such a position writes `begin` of the node it opens and `end` of the node it closes, for
+// every level at which it is a boundary; empty nodes keep the (0,0) of the memset.
+__global__ void __launch_bounds__(256) cell_table_kernel(const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, uint2 *__restrict__ table) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t code = sorted[i] >> gp.idxbits;
+        int top; // highest level at which position i opens a node
+        uint64_t prev = 0;
+        if (i == 0) {
+            top = gp.top_level;
+        } else {
+            prev = sorted[i - 1] >> gp.idxbits;
+            const uint64_t diff = code ^ prev;
+            top = diff ? min((63 - __clzll((long long)diff)) / 3, gp.top_level) : -1;
         }
-        const unsigned b = __ballot_sync(FULL_MASK, head);
-        rank[i] = running + __popc(b & lt);
-        running += __popc(b);
-        if (head) headbits |= 1u << i;
+        if (top >= 0) {
+            const uint32_t cx = compact3(code >> 2), cy = compact3(code >> 1), cz = compact3(code);
+            const uint32_t px = compact3(prev >> 2), py = compact3(prev >> 1), pz = compact3(prev);
+            for (int l = 0; l <= top; l++) {
+                table[table_index(gp, l, cx >> l, cy >> l, cz >> l)].x = i;
+                if (i > 0) table[table_index(gp, l, px >> l, py >> l, pz >> l)].y = i;
+            }
+        }
+        if (i == n - 1) {
+            const uint32_t cx = compact3(code >> 2), cy = compact3(code >> 1), cz = compact3(code);
+            for (int l = 0; l <= gp.top_level; l++) table[table_index(gp, l, cx >> l, cy >> l, cz >> l)].y = n;
+        }
     }
-    if (lane == 0) s_warp_total[warp] = running;
-    __syncthreads();
-    uint32_t warp_excl = 0, block_total = 0;
+}
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+/sm_100a PTX; SASS: UBLKCP / SYNCS) -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (!done) {
+            // a bulk copy completes in microseconds; fail loudly (sticky launch error) rather than hang the device
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000ll) __trap();
+        }
+    } while (!done);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- register sorting networks (fully unrolled, static indices only) ---------------------------------
+template <int N>
+__device__ __forceinline__ void bitonic_sort_asc(float (&a)[N]) {
 #pragma unroll
-    for (int w = 0; w < CH_THREADS / 32; w++) {
-        const uint32_t t = s_warp_total[w];
-        if (w < (int)warp) warp_excl += t;
-        block_total += t;
-    }
-    if (warp == 0) {
-        const uint32_t excl = lookback_exclusive(status, tile, block_total);
-        if (lane == 0) {
-            s_tile_excl = excl;
-            if (tile_base + CH_TILE >= n) {
-                *d_ncells = excl + block_total;
-                cell_start[excl + block_total] = n; // sentinel: end of the last cell
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+                    const bool up = (i & k) == 0;
+                    a[i] = up ? lo : hi;
+                    a[l] = up ? hi : lo;
+                }
             }
         }
     }
-    __syncthreads();
-    const uint32_t base = s_tile_excl + warp_excl;
+}
+template <int N>
+__device__ __forceinline__ void bitonic_merge_asc(float (&a)[N]) { // bitonic in, ascending out
 #pragma unroll
-    for (int i = 0; i < CH_ITEMS; i++) {
-        if (headbits & (1u << i)) {
-            cell_start[base + rank[i]] = warp_base + i * 32 + lane;
-            cell_code[base + rank[i]] = code[i];
+    for (int j = N >> 1; j > 0; j >>= 1) {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const int l = i ^ j;
+            if (l > i) {
+                const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+                a[i] = lo;
+                a[l] = hi;
+            }
         }
     }
-}
-
-// first index in code[0..n) with code[i] >= key
-__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t *__restrict__ code, uint32_t n, uint64_t key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (code[mid] < key) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
-// sorted insertion into an ascending register array: new[j] = min(best[j], max(best[j-1], d))
-template <int KCAP>
-__device__ __forceinline__ void topk_insert(float (&best)[KCAP], float d) {
-#pragma unroll
-    for (int j = KCAP - 1; j > 0; j--) best[j] = fminf(best[j], fmaxf(best[j - 1], d));
-    best[0] = fminf(best[0], d);
 }
 
 struct FarEntry {
-    uint32_t q;     // index in cell (sorted) order
-    uint32_t level; // level at which the query must be processed
-    float bound;    // valid upper bound on the (k+1)-th squared distance, +inf if unknown
+    uint32_t q;  // index in cell (sorted) order
+    float bound; // valid upper bound on the (k+1)-th squared distance, +inf if unknown
 };
 
-// smallest level l >= min_level whose pitch h*2^l covers sqrt(bound) (with slack); min_level if unbounded
-__device__ __forceinline__ uint32_t level_for_bound(float bound, float h, uint32_t min_level, uint32_t top_level) {
-    uint32_t l = min_level;
-    if (bound < INFINITY) {
-        const float r = sqrtf(bound) * 1.02f;
-        float pitch = ldexpf(h, (int)l);
-        while (l < top_level && pitch < r) {
-            l++;
-            pitch *= 2.f;
-        }
-    }
-    return min(l, top_level);
+// ---- main pass: one warp per 32 consecutive (cell-ordered) queries, one lane per query ---------------
+// Queries that share a level-2 node (a 4x4x4 block of cells) are processed together: their candidate
+// set is every cell within rc pitches of their common bounding box (at most 8x8x8 cells).  Lane 0
+// streams the candidates' 16-byte records into a double-buffered shared-memory ring with TMA bulk
+// copies (one per contiguous cell range); every lane then scans the same records as broadcast 128-bit
+// shared loads.  Per lane, distances below the running (k+1)-th best are parked in a shared-memory
+// column and merged into a sorted register array 16 at a time by bitonic networks, so the
+// per-candidate cost is a distance, a compare and a predicated store.
+constexpr int KT_WARPS = 8;
+constexpr int KT_THREADS = KT_WARPS * 32;
+constexpr int KT_CH = 128;     // candidates per stage
+constexpr int KT_STAGES = 2;
+constexpr int KT_MAXR = 512;   // cells of the largest candidate box
+constexpr int KT_BUF = 16;     // parked distances per lane
+
+struct __align__(128) KnnWarpSmem {
+    Point16 cand[KT_STAGES][KT_CH]; // 4096 B
+    float buf[KT_BUF][32];          // 2048 B
+    uint2 ranges[KT_MAXR];          // 4096 B
+    uint64_t mbar[KT_STAGES];
+};
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
 }
 
-// distance (in units of the level pitch) from u (cell units at that level) to the border of the
-// 3x3x3 block around cell c: min(u - (c-1), (c+2) - u)
-__device__ __forceinline__ float border_margin(float u, int c) { return fminf(u - (float)(c - 1), (float)(c + 2) - u); }
-
-// ---- level 0: warp per occupied cell, lane per query ----------------------------------------------
 template <int KCAP>
-__global__ void __launch_bounds__(128) knn_cell_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
-                                                        const uint32_t *__restrict__ cell_start, const uint64_t *__restrict__ cell_code,
-                                                        const uint32_t *__restrict__ d_ncells, float *__restrict__ dist_out, FarEntry *__restrict__ far_list,
-                                                        uint32_t *__restrict__ far_count) {
-    const unsigned lane = lane_id();
-    const uint32_t ncells = *d_ncells;
+__global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
+                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, FarEntry *__restrict__ far_list,
+                                                               uint32_t *__restrict__ far_count) {
+    extern __shared__ __align__(128) unsigned char knn_smem_raw[];
+    constexpr int B = KCAP < KT_BUF ? KCAP : KT_BUF;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    KnnWarpSmem &ws = reinterpret_cast<KnnWarpSmem *>(knn_smem_raw)[warp];
+    const unsigned lt = lanemask_lt();
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < KT_STAGES; st++) mbar_init(&ws.mbar[st], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase_bits = 0; // bit st: parity the next wait on stage st must see
+
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint64_t idxmask = (1ull << gp.idxbits) - 1ull;
     const int extra = KCAP - kk; // leading slots pinned at -inf so that best[KCAP-1] is the kk-th smallest
-    for (uint32_t cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < ncells; cell += warps_total) {
-        const uint32_t q_begin = cell_start[cell], q_end = cell_start[cell + 1];
-        const uint64_t code = cell_code[cell];
-        const int cx = (int)compact3(code >> 2), cy = (int)compact3(code >> 1), cz = (int)compact3(code);
-        // lanes 0..26 locate one neighbour cell each
-        uint32_t nb_begin = 0, nb_end = 0;
-        if (lane < 27) {
-            const int nx = cx + (int)(lane % 3) - 1, ny = cy + (int)((lane / 3) % 3) - 1, nz = cz + (int)(lane / 9) - 1;
-            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < gp.gdim[0] && ny < gp.gdim[1] && nz < gp.gdim[2]) {
-                const uint64_t ncode = morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
-                const uint32_t pos = lower_bound_u64(cell_code, ncells, ncode);
-                if (pos < ncells && cell_code[pos] == ncode) {
-                    nb_begin = cell_start[pos];
-                    nb_end = cell_start[pos + 1];
+    const uint32_t nitems = (n + 31u) >> 5;
+    const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
+    const float rc = gp.rc;
+    // every point within `reach` of a query is inside the scanned cells (0.01 pitch covers the rounding of cell_u)
+    const float reach = (rc - 0.01f) * gp.h;
+    const float reach2 = reach * reach * 0.999999f;
+
+    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += warps_total) {
+        const uint32_t qi = item * 32u + lane;
+        const bool active = qi < n;
+        const uint32_t qs = active ? qi : n - 1u;
+        const uint64_t word = sorted[qs];
+        const uint64_t code = word >> gp.idxbits;
+        const Point16 q = spts16[qs];
+        const float ux = cell_u(q.x, gp.gmin[0], gp.inv_h), uy = cell_u(q.y, gp.gmin[1], gp.inv_h), uz = cell_u(q.z, gp.gmin[2], gp.inv_h);
+
+        // groups: runs of lanes inside one level-2 node (codes are non-decreasing along the lanes)
+        const uint64_t node2 = code >> 6;
+        const uint64_t prev_node2 = __shfl_up_sync(FULL_MASK, node2, 1);
+        const unsigned heads = __ballot_sync(FULL_MASK, (lane == 0) || (node2 != prev_node2));
+        const int m = __popc(heads);
+        const int ord = __popc(heads & (lt | (1u << lane))) - 1;
+
+        for (int g = 0; g < m; g++) {
+            const bool live = active && ord == g;
+
+            // ---- bounding box of the group's queries (cell units) and the cells within rc of it ----
+            const float lox = warp_min(live ? ux : INFINITY), loy = warp_min(live ? uy : INFINITY), loz = warp_min(live ? uz : INFINITY);
+            const float hix = warp_max(live ? ux : -INFINITY), hiy = warp_max(live ? uy : -INFINITY), hiz = warp_max(live ? uz : -INFINITY);
+            uint32_t nr = 0, total = 0;
+            if (lox <= hix) { // the group has at least one live query (always, except for padding lanes)
+                const int cx0 = max((int)floorf(lox - rc), 0), cx1 = min((int)floorf(hix + rc), gp.gdim[0] - 1);
+                const int cy0 = max((int)floorf(loy - rc), 0), cy1 = min((int)floorf(hiy + rc), gp.gdim[1] - 1);
+                const int cz0 = max((int)floorf(loz - rc), 0), cz1 = min((int)floorf(hiz + rc), gp.gdim[2] - 1);
+                const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1, nbz = cz1 - cz0 + 1;
+                const int nb = nbx * nby * nbz; // <= 8*8*8: the queries span at most 4 cells per axis and rc <= 1.5
+                const float rc2 = rc * rc;
+                for (int t0 = 0; t0 < nb; t0 += 32) {
+                    const int t = t0 + (int)lane;
+                    uint2 r = make_uint2(0u, 0u);
+                    if (t < nb) {
+                        const int ix = cx0 + t % nbx, iy = cy0 + (t / nbx) % nby, iz = cz0 + t / (nbx * nby);
+                        const float dx = fmaxf(fmaxf((float)ix - hix, lox - (float)(ix + 1)), 0.f);
+                        const float dy = fmaxf(fmaxf((float)iy - hiy, loy - (float)(iy + 1)), 0.f);
+                        const float dz = fmaxf(fmaxf((float)iz - hiz, loz - (float)(iz + 1)), 0.f);
+                        if (dx * dx + dy * dy + dz * dz <= rc2) r = table[table_index(gp, 0, (uint32_t)ix, (uint32_t)iy, (uint32_t)iz)];
+                    }
+                    const unsigned has = __ballot_sync(FULL_MASK, r.y > r.x);
+                    if (r.y > r.x) ws.ranges[nr + __popc(has & lt)] = r;
+                    nr += __popc(has);
+                    total += warp_sum(r.y - r.x);
                 }
             }
-        }
-        for (uint32_t qb = q_begin; qb < q_end; qb += 32) {
-            const uint32_t qi = qb + lane;
-            const bool active = qi < q_end;
-            Point16 q = ld_point(spts, active ? qi : q_begin);
+            __syncwarp();
+
+            // ---- stream the candidates through the ring, keep the kk smallest distances per lane ----
             float best[KCAP];
 #pragma unroll
             for (int j = 0; j < KCAP; j++) best[j] = (j < extra) ? -INFINITY : INFINITY;
-            for (int nb = 0; nb < 27; nb++) {
-                const uint32_t cb = __shfl_sync(FULL_MASK, nb_begin, nb), ce = __shfl_sync(FULL_MASK, nb_end, nb);
-                for (uint32_t c = cb; c < ce; c++) {
-                    const Point16 cand = ld_point(spts, c); // same address in every lane: one broadcast load
-                    const float d2 = dist2(q, cand);
-                    if (d2 < best[KCAP - 1]) topk_insert<KCAP>(best, d2);
+            float tau = live ? INFINITY : -INFINITY;
+            uint32_t bcnt = 0;
+
+            const uint32_t nchunks = (total + KT_CH - 1) / KT_CH;
+            uint32_t ri = 0, roff = 0; // producer cursor (lane 0)
+            auto fill = [&](int st, uint32_t chunk) {
+                const uint32_t cnt = min((uint32_t)KT_CH, total - chunk * KT_CH);
+                mbar_arrive_expect_tx(&ws.mbar[st], cnt * 16u);
+                uint32_t filled = 0;
+                while (filled < cnt) {
+                    const uint2 r = ws.ranges[ri];
+                    const uint32_t len = r.y - r.x;
+                    const uint32_t take = min(len - roff, cnt - filled);
+                    bulk_g2s(&ws.cand[st][filled], spts16 + r.x + roff, take * 16u, &ws.mbar[st]);
+                    filled += take;
+                    roff += take;
+                    if (roff == len) {
+                        ri++;
+                        roff = 0;
+                    }
                 }
+            };
+            if (lane == 0 && nchunks > 0) {
+                fill(0, 0);
+                if (nchunks > 1) fill(1, 1);
             }
-            if (!active) continue;
-            // exact iff the kk-th distance does not reach the border of the 3x3x3 block
-            const float ux = cell_u(q.x, gp.gmin[0], gp.inv_h), uy = cell_u(q.y, gp.gmin[1], gp.inv_h), uz = cell_u(q.z, gp.gmin[2], gp.inv_h);
-            const float m = fminf(fminf(border_margin(ux, cx), border_margin(uy, cy)), border_margin(uz, cz)) - 0.01f;
-            const float reach = m * gp.h;
+            for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
+                const int st = (int)(chunk & 1u);
+                mbar_wait(&ws.mbar[st], (phase_bits >> st) & 1u);
+                phase_bits ^= 1u << st;
+                const uint32_t cnt = min((uint32_t)KT_CH, total - chunk * KT_CH);
+                const bool last_chunk = chunk + 1 == nchunks;
+                for (uint32_t c = 0; c < cnt; c += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (c + u < cnt) {
+                            const Point16 cand = ws.cand[st][c + u]; // same address in every lane: one broadcast load
+                            const float d2 = dist2(q, cand);
+                            if (d2 < tau) {
+                                ws.buf[bcnt][lane] = d2;
+                                bcnt++;
+                            }
+                        }
+                    }
+                    const bool finish = last_chunk && c + 4 >= cnt;
+                    if (finish || __any_sync(FULL_MASK, bcnt > (uint32_t)(B - 4))) {
+                        // merge the parked distances: sort them, keep the KCAP smallest of (best U parked), re-sort
+                        float s[B];
+#pragma unroll
+                        for (int j = 0; j < B; j++) s[j] = ((uint32_t)j < bcnt) ? ws.buf[j][lane] : INFINITY;
+                        bitonic_sort_asc<B>(s);
+#pragma unroll
+                        for (int j = 0; j < B; j++) best[KCAP - 1 - j] = fminf(best[KCAP - 1 - j], s[j]);
+                        bitonic_merge_asc<KCAP>(best);
+                        bcnt = 0;
+                        if (live) tau = best[KCAP - 1];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && chunk + 2 < nchunks) fill(st, chunk + 2);
+            }
+
+            if (!live) continue;
             const float worst = best[KCAP - 1];
-            if (gp.top_level == 0 || (m > 0.f && worst <= reach * reach * 0.999999f)) {
+            if (gp.top_level == 0 || worst <= reach2) {
                 double sum = 0.0;
 #pragma unroll
                 for (int j = 0; j < KCAP; j++)
                     if (j > extra) sum += sqrt((double)best[j]); // j == extra is the query itself (distance 0)
-                dist_out[(size_t)(sorted[qi] & idxmask)] = (float)(sum / (double)k);
+                dist_out[(size_t)(word & idxmask)] = (float)(sum / (double)k);
             } else {
                 const uint32_t slot = atomicAdd(far_count, 1u);
                 FarEntry e;
                 e.q = qi;
                 e.bound = worst;
-                e.level = level_for_bound(worst, gp.h, 1u, (uint32_t)gp.top_level);
                 far_list[slot] = e;
             }
         }
+        __syncwarp();
     }
 }
 
-// ---- levels >= 1: warp per queued query ----------------------------------------------------------
-template <int KCAP>
-__global__ void __launch_bounds__(128) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
-                                                       uint32_t level, const uint32_t *__restrict__ cell_start, const uint64_t *__restrict__ cell_code,
-                                                       const uint32_t *__restrict__ d_ncells, float *__restrict__ dist_out, FarEntry *__restrict__ far_list,
-                                                       const uint32_t *__restrict__ far_count) {
-    const unsigned lane = lane_id();
-    const uint32_t ncells = *d_ncells;
-    const uint32_t nentries = *far_count; // queued by level 0; entries are re-levelled in place
+// ---- far pass: queries the main pass could not prove exact, one warp each -----------------------------
+// Depth-first search of the table pyramid (an implicit octree: a node of level l is one contiguous
+// run of points), nearest child first, pruned by the running (k+1)-th best.  The best list lives
+// across the lanes (element e in lane e%32, register e/32) and absorbs 32 new distances at a time
+// through warp-shuffle bitonic networks.
+constexpr int KF_WARPS = 4;
+constexpr int KF_THREADS = KF_WARPS * 32;
+constexpr int KF_STACK = 112; // >= 7 * top_level + 8 with top_level <= 13
+
+struct FarNode { // 32 B
+    uint32_t pb, pe;  // point range
+    uint32_t x, y, z; // node coordinates at its level
+    int level;
+    float mind2;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ float warp_bitonic_sort32(float x, unsigned lane) { // ascending along the lanes
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float y = __shfl_xor_sync(FULL_MASK, x, j);
+            const bool up = (lane & (unsigned)k) == 0u; // k == 32: always ascending
+            const bool lower = (lane & (unsigned)j) == 0u;
+            x = (lower == up) ? fminf(x, y) : fmaxf(x, y);
+        }
+    }
+    return x;
+}
+__device__ __forceinline__ float warp_bitonic_merge32(float x, unsigned lane) { // bitonic in, ascending out
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const float y = __shfl_xor_sync(FULL_MASK, x, j);
+        x = ((lane & (unsigned)j) == 0u) ? fminf(x, y) : fmaxf(x, y);
+    }
+    return x;
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
+                                                              const uint2 *__restrict__ table, float *__restrict__ dist_out, const FarEntry *__restrict__ far_list,
+                                                              const uint32_t *__restrict__ far_count) {
+    __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    FarNode *stack = s_stack[warp];
+    const uint32_t nentries = *far_count;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint64_t idxmask = (1ull << gp.idxbits) - 1ull;
-    const float pitch = ldexpf(gp.h, (int)level);
-    const float inv_pitch = ldexpf(gp.inv_h, -(int)level);
+    const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
+    const float slack = 0.01f * gp.h;
+
     for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < nentries; ei += warps_total) {
         const FarEntry ent = far_list[ei];
-        if (ent.level != level) continue;
-        const Point16 q = ld_point(spts, ent.q);
-        const uint64_t code0 = sorted[ent.q] >> gp.idxbits;
-        const int cx = (int)(compact3(code0 >> 2) >> level), cy = (int)(compact3(code0 >> 1) >> level), cz = (int)(compact3(code0) >> level);
-        const float bound = ent.bound;
-        // lanes 0..26: candidate range of one level-`level` neighbour cell (a contiguous run of fine cells)
-        uint32_t nb_begin = 0, nb_end = 0;
-        if (lane < 27) {
-            const int nx = cx + (int)(lane % 3) - 1, ny = cy + (int)((lane / 3) % 3) - 1, nz = cz + (int)(lane / 9) - 1;
-            const int gx = (gp.gdim[0] - 1) >> level, gy = (gp.gdim[1] - 1) >> level, gz = (gp.gdim[2] - 1) >> level;
-            if (nx >= 0 && ny >= 0 && nz >= 0 && nx <= gx && ny <= gy && nz <= gz) {
-                bool wanted = true;
-                if (bound < INFINITY) {
-                    // squared distance from q to the neighbour's box; skip boxes beyond the known bound
-                    const float lo[3] = {gp.gmin[0] + (float)nx * pitch, gp.gmin[1] + (float)ny * pitch, gp.gmin[2] + (float)nz * pitch};
-                    const float qq[3] = {q.x, q.y, q.z};
-                    float bd2 = 0.f;
+        const Point16 q = spts16[ent.q];
+        const float limit = ent.bound; // at least kk points lie within `limit` when it is finite
+        float v[KPL];
 #pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        const float below = lo[a] - qq[a], above = qq[a] - (lo[a] + pitch);
-                        const float d = fmaxf(fmaxf(below, above), 0.f);
-                        bd2 += d * d;
+        for (int j = 0; j < KPL; j++) v[j] = INFINITY;
+        float tau = INFINITY; // current kk-th smallest
+
+        if (lane == 0) {
+            FarNode root;
+            root.pb = 0; root.pe = n; root.x = root.y = root.z = 0; root.level = gp.top_level; root.mind2 = 0.f; root.pad = 0;
+            stack[0] = root;
+        }
+        int sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            const FarNode node = stack[--sp];
+            __syncwarp();
+            const float thr = fminf(tau, limit);
+            if (node.mind2 * 0.9999f > thr) continue;
+            if (node.level == 0 || node.pe - node.pb <= 64u) {
+                for (uint32_t base = node.pb; base < node.pe; base += 32) {
+                    const uint32_t c = base + lane;
+                    float d2 = INFINITY;
+                    if (c < node.pe) d2 = dist2(q, spts16[c]);
+                    const bool pass = d2 < tau && d2 <= limit;
+                    if (!__any_sync(FULL_MASK, pass)) continue;
+                    const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
+                    const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
+                    if (KPL == 1) {
+                        v[0] = warp_bitonic_merge32(fminf(v[0], r), lane);
+                    } else {
+                        v[KPL - 1] = fminf(v[KPL - 1], r);
+                        const float lo = fminf(v[0], v[KPL - 1]), hi = fmaxf(v[0], v[KPL - 1]);
+                        v[0] = warp_bitonic_merge32(lo, lane);
+                        v[KPL - 1] = warp_bitonic_merge32(hi, lane);
                     }
-                    wanted = bd2 * 0.98f <= bound;
+                    tau = __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
                 }
-                if (wanted) {
-                    const uint64_t lo_code = morton3((uint32_t)nx, (uint32_t)ny, (uint32_t)nz) << (3 * level);
-                    const uint64_t hi_code = lo_code + (1ull << (3 * level));
-                    const uint32_t p0 = lower_bound_u64(cell_code, ncells, lo_code);
-                    const uint32_t p1 = lower_bound_u64(cell_code, ncells, hi_code);
-                    nb_begin = cell_start[p0];
-                    nb_end = cell_start[p1];
-                }
-            }
-        }
-        float best[KCAP];
+            } else {
+                // children at level-1: lanes 0..7 look one child up each
+                const int cl = node.level - 1;
+                const uint32_t chx = 2u * node.x + ((lane >> 2) & 1u), chy = 2u * node.y + ((lane >> 1) & 1u), chz = 2u * node.z + (lane & 1u);
+                uint2 r = make_uint2(0u, 0u);
+                float mind2 = INFINITY;
+                bool admit = false;
+                if (lane < 8 && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl)) {
+                    r = table[table_index(gp, cl, chx, chy, chz)];
+                    if (r.y > r.x) {
+                        const float pitch = ldexpf(gp.h, cl);
+                        const float lo[3] = {gp.gmin[0] + (float)chx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
+                        const float qq[3] = {q.x, q.y, q.z};
+                        mind2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < KCAP; j++) best[j] = INFINITY;
-        for (int nb = 0; nb < 27; nb++) {
-            const uint32_t cb = __shfl_sync(FULL_MASK, nb_begin, nb), ce = __shfl_sync(FULL_MASK, nb_end, nb);
-            for (uint32_t c = cb + lane; c < ce; c += 32) {
-                const float d2 = dist2(q, ld_point(spts, c));
-                if (d2 <= bound && d2 < best[KCAP - 1]) topk_insert<KCAP>(best, d2);
+                        for (int a = 0; a < 3; a++) {
+                            const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
+                            mind2 += d * d;
+                        }
+                        admit = mind2 * 0.9999f <= thr;
+                    }
+                }
+                const unsigned adm = __ballot_sync(FULL_MASK, admit);
+                const int nadm = __popc(adm);
+                int rank = 0; // position among the admitted children, nearest first
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float mj = __shfl_sync(FULL_MASK, mind2, j);
+                    if (((adm >> j) & 1u) && (mj < mind2 || (mj == mind2 && j < (int)lane))) rank++;
+                }
+                if (admit) {
+                    FarNode ch;
+                    ch.pb = r.x; ch.pe = r.y; ch.x = chx; ch.y = chy; ch.z = chz; ch.level = cl; ch.mind2 = mind2; ch.pad = 0;
+                    stack[sp + nadm - 1 - rank] = ch; // farthest deepest, nearest on top
+                }
+                sp += nadm;
+                __syncwarp();
             }
         }
-        // merge the 32 ascending lists: kk rounds of warp-min + pop at the winning lane
+        // sum of sqrt over elements 1..k in ascending order (double), as the reference does
+        double sq[KPL];
+#pragma unroll
+        for (int j = 0; j < KPL; j++) sq[j] = sqrt((double)v[j]);
         double sum = 0.0;
-        float worst = INFINITY;
-        bool enough = true;
-        for (int r = 0; r < kk; r++) {
-            float m = best[0];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL_MASK, m, o));
-            if (!(m < INFINITY)) {
-                enough = false;
-                break;
-            }
-            const unsigned winners = __ballot_sync(FULL_MASK, best[0] == m);
-            if ((int)lane == __ffs(winners) - 1) {
-#pragma unroll
-                for (int j = 0; j < KCAP - 1; j++) best[j] = best[j + 1];
-                best[KCAP - 1] = INFINITY;
-            }
-            if (r > 0) sum += sqrt((double)m); // r == 0 is the query itself
-            worst = m;
+        for (int e = 1; e <= k; e++) {
+            const double t = __shfl_sync(FULL_MASK, e < 32 ? sq[0] : sq[KPL - 1], e & 31);
+            sum += t;
         }
-        if (lane != 0) continue;
-        bool done = enough;
-        if (done && level < (uint32_t)gp.top_level) {
-            const float ux = cell_u(q.x, gp.gmin[0], inv_pitch), uy = cell_u(q.y, gp.gmin[1], inv_pitch), uz = cell_u(q.z, gp.gmin[2], inv_pitch);
-            const float m = fminf(fminf(border_margin(ux, cx), border_margin(uy, cy)), border_margin(uz, cz)) - 0.01f;
-            const float reach = m * pitch;
-            done = (m > 0.f) && (worst <= reach * reach * 0.999999f);
-        }
-        if (done || level >= (uint32_t)gp.top_level) {
-            // at the top level every point has been scanned; `enough` can only be false when n < kk,
-            // which the host excludes
-            dist_out[(size_t)(sorted[ent.q] & idxmask)] = (float)(sum / (double)k);
-        } else {
-            // still open: move the entry to a coarser level (strictly later launch), in place
-            FarEntry e;
-            e.q = ent.q;
-            e.bound = enough ? fminf(worst, bound) : bound;
-            e.level = level_for_bound(e.bound, gp.h, level + 1, (uint32_t)gp.top_level);
-            far_list[ei] = e;
-        }
+        if (lane == 0) dist_out[(size_t)(sorted[ent.q] & idxmask)] = (float)(sum / (double)k);
     }
 }
 
@@ -410,27 +585,51 @@ unsigned stream_grid(size_t n, int dev) {
     return (unsigned)std::max<size_t>(1, std::min(div_up(n, 256), (size_t)sm_count(dev) * 8));
 }
 
-// Grid pitch: ~1.6x the expected k-neighbour radius of a surface sampled at `spacing`.
-GridParams choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, float hint_spacing) {
+// Tunables of the pitch heuristic (results never depend on them).  CWIPC_CUDA_KNN_PITCH scales the
+// pitch relative to the expected k-neighbour radius; CWIPC_CUDA_KNN_RC is the cover radius in pitches.
+float env_float(const char *name, float dflt, float lo, float hi) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    const float v = (float)atof(e);
+    return (v >= lo && v <= hi) ? v : dflt;
+}
+
+struct GridPlan {
     GridParams gp;
+    size_t table_entries = 0;
+};
+
+// Pitch ~ a fraction of the expected k-neighbour radius of a surface sampled at `spacing`; the main
+// pass covers rc pitches around each query group.  The dense tables bound the number of cells.
+GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, float hint_spacing) {
+    static const float pitch_factor = env_float("CWIPC_CUDA_KNN_PITCH", 1.0f, 0.05f, 20.f);
+    static const float rc = env_float("CWIPC_CUDA_KNN_RC", 1.0f, 0.25f, 1.5f);
+    GridPlan plan;
+    GridParams &gp = plan.gp;
     memset(&gp, 0, sizeof(gp));
     const double ext[3] = {(double)gmax[0] - gmin[0], (double)gmax[1] - gmin[1], (double)gmax[2] - gmin[2]};
     double spacing = hint_spacing > 0.f ? (double)hint_spacing : 0.0;
+    const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
     if (!(spacing > 0.0)) {
         const double area = 2.0 * (ext[0] * ext[1] + ext[1] * ext[2] + ext[2] * ext[0]);
-        const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
         if (area > 0.0) spacing = std::sqrt(area / (double)n);
         else if (longest > 0.0) spacing = longest / (double)n;
         else spacing = 1.0;
     }
-    double h = spacing * std::sqrt((double)(k + 1) / 3.14159265358979) * 1.6;
-    const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
+    // expected k-neighbour radius on a surface: spacing * sqrt((k+1)/pi); reach of the main pass = rc * h
+    double h = spacing * std::sqrt((double)(k + 1) / 3.14159265358979) * (double)pitch_factor;
     gp.idxbits = std::max(1, bit_length((uint64_t)n - 1));
     const int max_axis_bits = std::min(13, (64 - gp.idxbits) / 3);
     if (!(h > 0.0) || !std::isfinite(h)) h = 1.0;
-    while (longest / h >= (double)((1 << max_axis_bits) - 1)) h *= 2.0;
+    const double cell_cap = (double)std::min<size_t>(std::max<size_t>(4 * n, (size_t)1 << 16), (size_t)1 << 25);
+    while (true) {
+        const double cells = (std::floor(ext[0] / h) + 2) * (std::floor(ext[1] / h) + 2) * (std::floor(ext[2] / h) + 2);
+        if (longest / h < (double)((1 << max_axis_bits) - 1) && cells <= cell_cap) break;
+        h *= 1.25;
+    }
     gp.h = (float)h;
     gp.inv_h = 1.0f / gp.h;
+    gp.rc = rc;
     int maxdim = 1;
     for (int a = 0; a < 3; a++) {
         gp.gmin[a] = gmin[a];
@@ -438,23 +637,32 @@ GridParams choose_grid(const float gmin[3], const float gmax[3], size_t n, int k
         maxdim = std::max(maxdim, gp.gdim[a]);
     }
     gp.top_level = bit_length((uint64_t)maxdim - 1); // (gdim-1) >> top_level == 0 on every axis
-    return gp;
+    size_t off = 0;
+    for (int l = 0; l <= gp.top_level; l++) {
+        gp.table_off[l] = (uint32_t)off;
+        off += (size_t)level_dim(gp.gdim[0], l) * level_dim(gp.gdim[1], l) * level_dim(gp.gdim[2], l);
+    }
+    plan.table_entries = off;
+    return plan;
 }
 
 template <int KCAP>
-void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const GridParams &gp, int k, const uint32_t *cell_start, const uint64_t *cell_code,
-             const uint32_t *d_ncells, float *d_dist, FarEntry *far_list, uint32_t *far_count, int dev, cudaStream_t s) {
+void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const GridParams &gp, int k, const uint2 *table, float *d_dist, FarEntry *far_list,
+             uint32_t *far_count, int dev, cudaStream_t s) {
     const int kk = k + 1;
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(n, (size_t)32), (size_t)sm_count(dev) * 16));
-    launch("knn_cell_kernel", s, 28 * (size_t)n, [&] {
-        knn_cell_kernel<KCAP><<<grid, 128, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, cell_start, cell_code, d_ncells, d_dist, far_list, far_count);
+    const size_t smem = sizeof(KnnWarpSmem) * KT_WARPS;
+    static std::once_flag once[64];
+    std::call_once(once[dev & 63], [&] { CWCU_CHECK(cudaFuncSetAttribute(knn_tile_kernel<KCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+    const size_t nitems = div_up(n, (size_t)32);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nitems, (size_t)KT_WARPS), (size_t)sm_count(dev) * 2));
+    launch("knn_tile_kernel", s, 28 * (size_t)n, [&] {
+        knn_tile_kernel<KCAP><<<grid, KT_THREADS, smem, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, far_list, far_count);
     });
-    for (int level = 1; level <= gp.top_level; level++) {
-        launch("knn_far_kernel", s, (size_t)0, [&] {
-            knn_far_kernel<KCAP><<<(unsigned)sm_count(dev) * 8, 128, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, (uint32_t)level, cell_start, cell_code, d_ncells, d_dist,
-                                                                            far_list, far_count);
-        });
-    }
+    if (gp.top_level == 0) return; // one cell spans the cloud: the main pass is exact for every query
+    constexpr int KPL = KCAP > 32 ? 2 : 1;
+    launch("knn_far_kernel", s, (size_t)0, [&] {
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 4, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, far_list, far_count);
+    });
 }
 
 } // namespace
@@ -468,7 +676,8 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     global_bbox(in, n, gmin, gmax, dev, s);
     for (int a = 0; a < 3; a++)
         if (!std::isfinite(gmin[a]) || !std::isfinite(gmax[a])) throw CudaError{cudaErrorInvalidValue, "remove_outliers: pointcloud contains non-finite coordinates"};
-    const GridParams gp = choose_grid(gmin, gmax, n, k, hint_spacing);
+    const GridPlan plan = choose_grid(gmin, gmax, n, k, hint_spacing);
+    const GridParams &gp = plan.gp;
     int axis_bits = 1;
     for (int a = 0; a < 3; a++) axis_bits = std::max(axis_bits, bit_length((uint64_t)gp.gdim[a] - 1));
     const int keybits = 3 * axis_bits;
@@ -480,26 +689,17 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     Scratch spts(n * sizeof(cwipc_point), s);
     launch("knn_gather_kernel", s, 40 * (size_t)n, [&] { knn_gather_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, in, spts.as<cwipc_point>()); });
 
-    // occupied cells
-    const size_t ntiles = div_up(n, CH_TILE);
-    Scratch cell_start((n + 1) * sizeof(uint32_t), s), cell_code(n * sizeof(uint64_t), s);
-    // [ticket | ncells | far_count | pad] u32*4 then status u64*ntiles
-    const size_t aux_bytes = 16 + ntiles * sizeof(uint64_t);
-    Scratch aux(aux_bytes, s);
-    CWCU_CHECK(cudaMemsetAsync(aux.p, 0, aux_bytes, s));
-    uint32_t *ticket = aux.as<uint32_t>();
-    uint32_t *d_ncells = ticket + 1, *far_count = ticket + 2;
-    uint64_t *status = reinterpret_cast<uint64_t *>(ticket + 4);
-    launch("cell_heads_kernel", s, 8 * (size_t)n, [&] {
-        cell_heads_kernel<<<(unsigned)ntiles, CH_THREADS, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, cell_start.as<uint32_t>(), cell_code.as<uint64_t>(), ticket, status, d_ncells);
-    });
+    // table pyramid + far-query counter
+    Scratch table(plan.table_entries * sizeof(uint2) + 16, s);
+    CWCU_CHECK(cudaMemsetAsync(table.p, 0, plan.table_entries * sizeof(uint2) + 16, s));
+    uint32_t *far_count = reinterpret_cast<uint32_t *>(table.as<uint2>() + plan.table_entries);
+    launch("cell_table_kernel", s, 8 * (size_t)n, [&] { cell_table_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp, table.as<uint2>()); });
 
-    // a query is queued at most once (by level 0) and re-levelled in place afterwards
+    // a query is queued at most once
     Scratch far_list((n + 64) * sizeof(FarEntry), s);
     const int kk = k + 1;
     auto go = [&](auto kcap) {
-        run_knn<decltype(kcap)::value>(spts.as<cwipc_point>(), sorted, n, gp, k, cell_start.as<uint32_t>(), cell_code.as<uint64_t>(), d_ncells, d_dist,
-                                       far_list.as<FarEntry>(), far_count, dev, s);
+        run_knn<decltype(kcap)::value>(spts.as<cwipc_point>(), sorted, n, gp, k, table.as<uint2>(), d_dist, far_list.as<FarEntry>(), far_count, dev, s);
     };
     if (kk <= 8) go(std::integral_constant<int, 8>{});
     else if (kk <= 16) go(std::integral_constant<int, 16>{});

@@ -1,0 +1,9 @@
+set -x
+for w in 1 2 4 8 16; do
+  timeout 300 python bench.py --steps 5 --warmup 3 --workers $w --cpu-frames 1 > gpurun_out/sweep_w$w.json 2> gpurun_out/sweep_w$w.err; echo exit=$?
+  python - <<PY
+import json
+d=json.load(open("gpurun_out/sweep_w$w.json"))
+print("workers",$w,"value",d["value"],"e2e",d["e2e"]["value"],"step_ms",d["step_ms"],"e2e_ms",d["e2e_step_ms"])
+PY
+done

@@ -340,6 +340,35 @@ def test_knn_random_volume_duplicates_and_far_outliers(cw, orc):
         assert np.array_equal(cw.util.knn_mean_distances(upload(cw, pts), k), orc.knn_mean_distances(pts, k))
 
 
+@pytest.mark.parametrize("k", [1, 7, 8, 15, 16, 31, 32, 40, 63])
+def test_knn_every_list_width(cw, orc, k):
+    """k+1 on both sides of every register-list width (8/16/32/64) and of the 32-lane far list."""
+    pts = synthetic.add_outliers(synthetic.camera_cloud(20000, seed=k), 0.02, seed=k)
+    assert np.array_equal(cw.util.knn_mean_distances(upload(cw, pts, cellsize=0.004), k), orc.knn_mean_distances(pts, k))
+
+
+def test_knn_mostly_far_queries_and_dense_cells(cw, orc):
+    """A pitch far too small (every query goes through the octree search), one far too large (a handful of
+    cells, thousands of candidates per stage ring), and clumps denser than one TMA stage."""
+    rng = np.random.default_rng(5)
+    pts = random_cloud(30000, seed=11, extent=0.5)
+    clump = rng.integers(0, 30000, 40)
+    for j, c in enumerate(clump):          # 40 clumps of 150 near-identical points
+        sl = slice(j * 150, (j + 1) * 150)
+        for a in "xyz":
+            pts[a][sl] = pts[a][c] + rng.normal(0, 1e-4, 150).astype(np.float32)
+    want = orc.knn_mean_distances(pts, 30)
+    for cellsize in (1e-4, 0.0, 0.2):
+        assert np.array_equal(cw.util.knn_mean_distances(upload(cw, pts, cellsize=cellsize), 30), want), cellsize
+
+
+@pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 64, 65, 1000])
+def test_knn_tiny_clouds(cw, orc, n):
+    pts = random_cloud(n, seed=n, extent=0.1)
+    k = min(30, n - 1)
+    assert np.array_equal(cw.util.knn_mean_distances(upload(cw, pts), k), orc.knn_mean_distances(pts, k))
+
+
 def keepmask_check(pts, got, want_d, k, mul):
     """got must equal pts[keep] with keep decided by the oracle's distances, except within 1e-6 of the threshold."""
     d = want_d.astype(np.float64)
