@@ -233,6 +233,7 @@ struct KeyParams {
     // octree mode
     double omin[3];
     double res;
+    double inv_res;   // 1.0 / res (filter only; ties are decided by the exact division)
     double inv_cs;    // 1.0 / (double)cellsize
     int depth;
     // single-grid mode
@@ -267,7 +268,12 @@ __device__ __forceinline__ uint64_t voxel_key(const Point16 &p, const KeyParams 
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         // OctreePointCloud::genOctreeKeyforPoint: (unsigned)((double)x - min) / res), double arithmetic
-        const double rel = ((double)c[a] - kp.omin[a]) / kp.res;
+        // The quotient is only needed truncated: multiply by the reciprocal, and redo it with the exact
+        // division whenever the product lands within 1e-9 of a leaf face (the two differ by < 1e-11).
+        const double num = (double)c[a] - kp.omin[a];
+        double rel = num * kp.inv_res;
+        const double fr = rel - floor(rel);
+        if (!(fr > 1e-9 && fr < 1.0 - 1e-9)) rel = num / kp.res;
         leaf[a] = (uint32_t)rel;
         // Any per-leaf constant keeps the (z,y,x) order inside a leaf; this one is <= every voxel
         // coordinate that can occur in the leaf, and the leaf spans < 70 voxels.
@@ -292,212 +298,145 @@ __global__ void __launch_bounds__(256) voxel_keygen_kernel(const cwipc_point *__
     if (bad) atomicOr(error_flag, 1u);
 }
 
-// ---- segmented reduction of sorted runs --------------------------------------------------------
-constexpr int VR_THREADS = 256;
-constexpr int VR_ITEMS = 4;
-constexpr int VR_TILE = VR_THREADS * VR_ITEMS; // 1024 sorted elements per tile
+// ---- accumulation: one pass over the points into a hash table of voxels -------------------------------
+// Every voxel owns one 64-byte slot (one L2 line sector pair): key, fixed-point coordinate sums, colour
+// sums, point count and tile OR.  A warp first merges runs of equal keys among its 32 consecutive
+// points with a segmented shuffle scan (camera and scan-order clouds are spatially coherent, so runs
+// are long), then the last lane of every run finds or claims the slot (64-bit CAS, linear probing)
+// and adds its partial sums with fire-and-forget L2 atomics (RED).  Sums are integers, so the result
+// does not depend on the order in which points arrive (deterministic).  The thread that claims a
+// slot appends [key | slot] to the list the radix sort orders afterwards.
+struct __align__(64) VoxelSlot {
+    unsigned long long keyp1;      // key + 1; 0 = empty
+    unsigned long long sx, sy, sz; // two's-complement fixed-point sums
+    unsigned long long rg;         // sum r | sum g << 32
+    unsigned long long bn;         // sum b | count << 32
+    uint32_t tile;                 // OR of the tile bytes
+    uint32_t pad[3];
+};
+static_assert(sizeof(VoxelSlot) == 64, "one slot per 64 bytes");
 
-struct VoxelAgg { // 40 bytes
-    unsigned long long sx, sy, sz; // two's-complement fixed point sums
-    unsigned long long rgb;        // r | g<<21 | b<<42  (per-tile partials: 255*1024 < 2^21)
-    uint32_t n;
-    uint32_t tile;
+struct TableHeader { // first 64 bytes of the zeroed workspace
+    uint32_t count; // claimed slots
+    uint32_t error; // out-of-range coordinate seen
+    uint32_t pad[14];
 };
 
-struct TileRecord { // written by every tile, read by the fix-up
-    uint32_t base;      // global number of the tile's first run
-    uint32_t heads;     // runs starting in this tile
-    uint32_t tail_open; // last run continues in the next tile
-    uint32_t pad;
-};
+__device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (uint32_t)k;
+}
 
-struct WideAgg { // carries across tiles can exceed the packed rgb field: keep r,g,b apart
-    long long sx, sy, sz;
-    unsigned long long r, g, b;
-    unsigned long long n;
-    uint32_t tile;
-    uint32_t pad;
-};
+constexpr int VA_THREADS = 256;
 
-__device__ __forceinline__ void wide_add(WideAgg &w, const VoxelAgg &a) {
-    w.sx += (long long)a.sx;
-    w.sy += (long long)a.sy;
-    w.sz += (long long)a.sz;
-    w.r += a.rgb & 0x1fffffull;
-    w.g += (a.rgb >> 21) & 0x1fffffull;
-    w.b += (a.rgb >> 42) & 0x1fffffull;
-    w.n += a.n;
-    w.tile |= a.tile;
+__global__ void __launch_bounds__(VA_THREADS) voxel_accumulate_kernel(const cwipc_point *__restrict__ pts, uint32_t n, KeyParams kp, double scale, VoxelSlot *__restrict__ table,
+                                                                       uint32_t slot_mask, int slotbits, uint64_t *__restrict__ list, TableHeader *__restrict__ header) {
+    bool bad = false;
+    const unsigned lane = lane_id();
+    const unsigned le = lanemask_lt() | (1u << lane);
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        uint64_t key = ~0ull;
+        long long fx = 0, fy = 0, fz = 0;
+        unsigned long long rg = 0, bn = 0;
+        uint32_t tl = 0;
+        if (valid) {
+            const Point16 p = ld_point_stream(pts, i);
+            key = voxel_key(p, kp, &bad);
+            fx = __double2ll_rn((double)p.x * scale);
+            fy = __double2ll_rn((double)p.y * scale);
+            fz = __double2ll_rn((double)p.z * scale);
+            rg = (unsigned long long)pt_r(p) | ((unsigned long long)pt_g(p) << 32);
+            bn = (unsigned long long)pt_b(p) | (1ull << 32);
+            tl = pt_tile(p);
+        }
+        // runs of equal keys along the lanes -> inclusive segmented sums; the last lane of a run owns the total
+        const uint64_t prev = __shfl_up_sync(FULL_MASK, key, 1);
+        const unsigned heads = __ballot_sync(FULL_MASK, lane == 0 || key != prev);
+        const int seg_start = 31 - __clz(heads & le);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long tx = __shfl_up_sync(FULL_MASK, fx, o), ty = __shfl_up_sync(FULL_MASK, fy, o), tz = __shfl_up_sync(FULL_MASK, fz, o);
+            const unsigned long long trg = __shfl_up_sync(FULL_MASK, rg, o), tbn = __shfl_up_sync(FULL_MASK, bn, o);
+            const uint32_t tt = __shfl_up_sync(FULL_MASK, tl, o);
+            if ((int)lane - o >= seg_start) {
+                fx += tx;
+                fy += ty;
+                fz += tz;
+                rg += trg;
+                bn += tbn;
+                tl |= tt;
+            }
+        }
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (valid && tail) {
+            const unsigned long long want = key + 1ull;
+            uint32_t slot = hash_key(key) & slot_mask;
+            while (true) {
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&table[slot].keyp1);
+                if (cur == 0ull) {
+                    cur = atomicCAS(&table[slot].keyp1, 0ull, want);
+                    if (cur == 0ull) { // claimed: one list entry per voxel
+                        list[atomicAdd(&header->count, 1u)] = (key << slotbits) | slot;
+                        break;
+                    }
+                }
+                if (cur == want) break;
+                slot = (slot + 1u) & slot_mask;
+            }
+            VoxelSlot *sl = table + slot;
+            atomicAdd(&sl->sx, (unsigned long long)fx);
+            atomicAdd(&sl->sy, (unsigned long long)fy);
+            atomicAdd(&sl->sz, (unsigned long long)fz);
+            atomicAdd(&sl->rg, rg);
+            atomicAdd(&sl->bn, bn);
+            atomicOr(&sl->tile, tl);
+        }
+    }
+    if (bad) atomicOr(&header->error, 1u);
 }
 
 // mean xyz (exact sum, one rounding), truncated float colour average as pcl::CentroidPoint, OR of tiles
-__device__ __forceinline__ Point16 finalize_voxel(const WideAgg &w, double inv_scale) {
+__device__ __forceinline__ Point16 finalize_voxel(long long sx, long long sy, long long sz, unsigned long long sr, unsigned long long sg, unsigned long long sb,
+                                                   unsigned long long cnt, uint32_t tile, double inv_scale) {
     Point16 o;
-    const double dn = (double)w.n;
-    o.x = (float)(((double)w.sx * inv_scale) / dn);
-    o.y = (float)(((double)w.sy * inv_scale) / dn);
-    o.z = (float)(((double)w.sz * inv_scale) / dn);
-    const float fn = (float)w.n;
-    const uint32_t r = (uint32_t)__fdiv_rn((float)w.r, fn) & 0xffu;
-    const uint32_t g = (uint32_t)__fdiv_rn((float)w.g, fn) & 0xffu;
-    const uint32_t b = (uint32_t)__fdiv_rn((float)w.b, fn) & 0xffu;
-    o.rgbt = r | (g << 8) | (b << 16) | ((w.tile & 0xffu) << 24);
+    const double dn = (double)cnt;
+    o.x = (float)(((double)sx * inv_scale) / dn);
+    o.y = (float)(((double)sy * inv_scale) / dn);
+    o.z = (float)(((double)sz * inv_scale) / dn);
+    const float fn = (float)cnt;
+    const uint32_t r = (uint32_t)__fdiv_rn((float)sr, fn) & 0xffu;
+    const uint32_t g = (uint32_t)__fdiv_rn((float)sg, fn) & 0xffu;
+    const uint32_t b = (uint32_t)__fdiv_rn((float)sb, fn) & 0xffu;
+    o.rgbt = r | (g << 8) | (b << 16) | ((tile & 0xffu) << 24);
     return o;
 }
 
-__global__ void __launch_bounds__(VR_THREADS) voxel_reduce_kernel(const uint64_t *__restrict__ sorted, uint32_t n, int idxbits, const cwipc_point *__restrict__ pts,
-                                                                   double scale, double inv_scale, cwipc_point *__restrict__ out, uint32_t *__restrict__ ticket,
-                                                                   uint64_t *__restrict__ status, TileRecord *__restrict__ records, VoxelAgg *__restrict__ carry_head,
-                                                                   VoxelAgg *__restrict__ carry_tail, uint32_t *__restrict__ done_counter, uint32_t ntiles,
-                                                                   uint32_t *__restrict__ d_total) {
-    __shared__ VoxelAgg s_slot[VR_TILE + 1]; // slot 0: continuation of the previous tile's run; slot j: j-th run starting here
-    __shared__ uint32_t s_warp[VR_THREADS / 32];
-    __shared__ int s_tile;
-    __shared__ uint32_t s_base;
-    __shared__ bool s_last_block;
-
-    if (threadIdx.x == 0) s_tile = take_ticket(ticket);
-    __syncthreads();
-    const int tile = s_tile;
-    const uint32_t tile_base = (uint32_t)tile * VR_TILE;
-    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    const uint64_t idxmask = (1ull << idxbits) - 1ull;
-
-    // ---- keys of my 4 consecutive elements, head flags ----
-    const uint32_t e0 = tile_base + threadIdx.x * VR_ITEMS;
-    uint64_t k[VR_ITEMS];
-    bool head[VR_ITEMS];
-    uint64_t prev = (e0 > 0 && e0 <= n) ? (sorted[e0 - 1] >> idxbits) : ~0ull;
-    uint32_t nheads = 0;
-#pragma unroll
-    for (int j = 0; j < VR_ITEMS; j++) {
-        const uint32_t e = e0 + j;
-        if (e < n) {
-            k[j] = sorted[e];
-            const uint64_t kk = k[j] >> idxbits;
-            head[j] = (e == 0) || (kk != prev);
-            prev = kk;
-            nheads += head[j] ? 1u : 0u;
-        } else {
-            k[j] = 0;
-            head[j] = false;
-        }
-    }
-    // block exclusive scan of head counts
-    const uint32_t incl = warp_inclusive_scan(nheads);
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t warp_off = 0, H = 0;
-#pragma unroll
-    for (int w = 0; w < VR_THREADS / 32; w++) {
-        const uint32_t t = s_warp[w];
-        if (w < (int)warp) warp_off += t;
-        H += t;
-    }
-    uint32_t slot = warp_off + incl - nheads; // heads before my first element == slot of a non-head first element
-
-    // zero the slots in use
-    for (uint32_t j = threadIdx.x; j <= H; j += VR_THREADS) {
-        s_slot[j].sx = 0; s_slot[j].sy = 0; s_slot[j].sz = 0; s_slot[j].rgb = 0; s_slot[j].n = 0; s_slot[j].tile = 0;
-    }
-    // chained numbering of runs across tiles (warp 0), overlapped with the gathers below
-    __syncthreads();
-
-    // ---- gather points, accumulate sequentially, flush a partial whenever a run ends ----
-    Point16 p[VR_ITEMS];
-#pragma unroll
-    for (int j = 0; j < VR_ITEMS; j++)
-        if (e0 + j < n) p[j] = ld_point(pts, (size_t)(k[j] & idxmask));
-
-    long long ax = 0, ay = 0, az = 0;
-    unsigned long long argb = 0;
-    uint32_t an = 0, at = 0;
-    auto flush = [&](uint32_t s) {
-        if (an) {
-            atomicAdd(&s_slot[s].sx, (unsigned long long)ax);
-            atomicAdd(&s_slot[s].sy, (unsigned long long)ay);
-            atomicAdd(&s_slot[s].sz, (unsigned long long)az);
-            atomicAdd(&s_slot[s].rgb, argb);
-            atomicAdd(&s_slot[s].n, an);
-            atomicOr(&s_slot[s].tile, at);
-        }
-        ax = ay = az = 0;
-        argb = 0;
-        an = at = 0;
-    };
-#pragma unroll
-    for (int j = 0; j < VR_ITEMS; j++) {
-        if (e0 + j < n) {
-            if (head[j]) {
-                flush(slot);
-                slot++;
-            }
-            ax += __double2ll_rn((double)p[j].x * scale);
-            ay += __double2ll_rn((double)p[j].y * scale);
-            az += __double2ll_rn((double)p[j].z * scale);
-            argb += (unsigned long long)pt_r(p[j]) | ((unsigned long long)pt_g(p[j]) << 21) | ((unsigned long long)pt_b(p[j]) << 42);
-            an += 1;
-            at |= pt_tile(p[j]);
-        }
-    }
-    flush(slot);
-
-    if (warp == 0) {
-        const uint32_t excl = lookback_exclusive(status, tile, H);
-        if (lane == 0) s_base = excl;
-    }
-    __syncthreads();
-    const uint32_t base = s_base;
-
-    // does the run that is open at the end of this tile continue in the next one?
-    const uint32_t tile_end = min(tile_base + VR_TILE, n);
-    bool tail_open = false;
-    if (tile_end < n) tail_open = (sorted[tile_end] >> idxbits) == (sorted[tile_end - 1] >> idxbits);
-
-    // ---- emit complete runs; park partial ones for the fix-up ----
-    for (uint32_t j = threadIdx.x; j <= H; j += VR_THREADS) {
-        const VoxelAgg a = s_slot[j];
-        if (j == 0) {
-            carry_head[tile] = a; // may be empty (n == 0)
-        } else if (j == H && tail_open) {
-            carry_tail[tile] = a;
-        } else {
-            WideAgg w = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            wide_add(w, a);
-            st_point(out, base + j - 1, finalize_voxel(w, inv_scale));
-        }
-    }
-    if (H == 0 && threadIdx.x == 0) {
-        // whole tile continues an older run: nothing starts here
-    }
-    if (threadIdx.x == 0) {
-        TileRecord r;
-        r.base = base;
-        r.heads = H;
-        r.tail_open = (H > 0 && tail_open) ? 1u : 0u;
-        r.pad = 0;
-        records[tile] = r;
-        if (tile_end >= n) *d_total = base + H;
-    }
-
-    // ---- last block to finish merges the runs that cross tile boundaries ----
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last_block = (atomicAdd(done_counter, 1u) == ntiles - 1);
-    __syncthreads();
-    if (!s_last_block) return;
-    __threadfence();
-    for (uint32_t t = threadIdx.x; t < ntiles; t += VR_THREADS) {
-        const TileRecord r = records[t];
-        if (!r.tail_open) continue;
-        WideAgg w = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        wide_add(w, carry_tail[t]);
-        for (uint32_t u = t + 1; u < ntiles; u++) {
-            wide_add(w, carry_head[u]);
-            if (records[u].heads != 0) break; // the run ends inside tile u
-        }
-        st_point(out, r.base + r.heads - 1, finalize_voxel(w, inv_scale));
-    }
+// One output point per sorted list entry; the slot is read once and cleared, so the table is all zero
+// again when the kernel ends (no memset between calls).
+__global__ void __launch_bounds__(256) voxel_emit_kernel(const uint64_t *__restrict__ sorted, uint32_t v, uint32_t slot_mask, VoxelSlot *__restrict__ table, double inv_scale,
+                                                          cwipc_point *__restrict__ out, TableHeader *__restrict__ header) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) header->count = 0;
+    if (j >= v) return;
+    VoxelSlot *sl = table + (uint32_t)(sorted[j] & (uint64_t)slot_mask);
+    uint4 *raw = reinterpret_cast<uint4 *>(sl);
+    const uint4 a = raw[0], b = raw[1], c = raw[2], d = raw[3];
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    raw[0] = zero;
+    raw[1] = zero;
+    raw[2] = zero;
+    raw[3] = zero;
+    const long long sx = (long long)(((unsigned long long)a.w << 32) | a.z);
+    const long long sy = (long long)(((unsigned long long)b.y << 32) | b.x);
+    const long long sz = (long long)(((unsigned long long)b.w << 32) | b.z);
+    st_point(out, j, finalize_voxel(sx, sy, sz, c.x, c.y, c.z, c.w, d.x, inv_scale));
 }
 
 int bit_length(uint64_t v) {
@@ -515,6 +454,9 @@ struct Plan {
     bool failed = false;
     std::string error;
     float maxabs = 0.f;
+    float gmin[3] = {0, 0, 0}, gmax[3] = {0, 0, 0};
+    size_t capacity = 0; // hash table slots (power of two)
+    int slotbits = 0;
 };
 
 // Runs the two bounding-box kernels, reads the box back (one sync) and derives the key layout.
@@ -540,7 +482,14 @@ Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_spl
     kp.octree = octree_split ? 1 : 0;
     kp.inv = 1.0f / cellsize;
     kp.idxbits = std::max(1, bit_length((uint64_t)n - 1));
-    for (int a = 0; a < 3; a++) plan.maxabs = std::max(plan.maxabs, std::max(std::fabs(ob.gmin[a]), std::fabs(ob.gmax[a])));
+    for (int a = 0; a < 3; a++) {
+        plan.maxabs = std::max(plan.maxabs, std::max(std::fabs(ob.gmin[a]), std::fabs(ob.gmax[a])));
+        plan.gmin[a] = ob.gmin[a];
+        plan.gmax[a] = ob.gmax[a];
+    }
+    plan.capacity = 1024;
+    while (plan.capacity < n + n / 2) plan.capacity <<= 1;
+    plan.slotbits = bit_length((uint64_t)plan.capacity - 1);
     if (!std::isfinite(plan.maxabs)) {
         plan.failed = true;
         plan.error = "pointcloud contains non-finite coordinates";
@@ -554,6 +503,7 @@ Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_spl
         }
         for (int a = 0; a < 3; a++) kp.omin[a] = ob.min[a];
         kp.res = res;
+        kp.inv_res = 1.0 / res;
         kp.inv_cs = 1.0 / (double)cellsize;
         kp.depth = ob.depth;
         plan.keybits = WL_BITS + 3 * ob.depth;
@@ -578,9 +528,9 @@ Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_spl
         }
         plan.keybits = std::max(1, bit_length(cells - 1));
     }
-    if (plan.keybits + kp.idxbits > 64) {
+    if (plan.keybits + plan.slotbits > 64) {
         plan.failed = true;
-        plan.error = "pointcloud too large for 64-bit voxel keys (" + std::to_string(plan.keybits) + " key bits + " + std::to_string(kp.idxbits) + " index bits)";
+        plan.error = "pointcloud too large for 64-bit voxel keys (" + std::to_string(plan.keybits) + " key bits + " + std::to_string(plan.slotbits) + " slot bits)";
     }
     return plan;
 }
@@ -618,12 +568,6 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
     }
     const KeyParams &kp = plan.kp;
 
-    Scratch keys_a(n * sizeof(uint64_t), s), keys_b(n * sizeof(uint64_t), s);
-    Scratch flag(sizeof(uint32_t), s);
-    CWCU_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
-    launch("voxel_keygen_kernel", s, 24 * (size_t)n, [&] { voxel_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in->d_pts, (uint32_t)n, kp, keys_a.as<uint64_t>(), 1, flag.as<uint32_t>()); });
-    uint64_t *sorted = radix_sort_u64(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), n, kp.idxbits, kp.idxbits + plan.keybits, dev, s);
-
     // fixed-point scale: |x| * 2^shift * n < 2^62
     int shift = 62 - bit_length((uint64_t)n);
     if (plan.maxabs > 0.f) {
@@ -634,38 +578,46 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
     shift = std::max(-60, std::min(shift, 100));
     const double scale = std::ldexp(1.0, shift), inv_scale = std::ldexp(1.0, -shift);
 
-    const uint32_t ntiles = (uint32_t)div_up(n, VR_TILE);
-    // [ticket | done | total | pad] u32*4, status u64*ntiles, records, carry_head, carry_tail
-    const size_t off_status = 16;
-    const size_t off_records = off_status + (size_t)ntiles * sizeof(uint64_t);
-    const size_t off_head = off_records + (size_t)ntiles * sizeof(TileRecord);
-    const size_t off_tail = off_head + (size_t)ntiles * sizeof(VoxelAgg);
-    const size_t bytes = off_tail + (size_t)ntiles * sizeof(VoxelAgg);
-    Scratch aux(bytes, s);
-    CWCU_CHECK(cudaMemsetAsync(aux.p, 0, off_records, s));
-    uint8_t *ab = aux.as<uint8_t>();
-    uint32_t *ticket = reinterpret_cast<uint32_t *>(ab);
-    uint32_t *done = ticket + 1, *d_total = ticket + 2;
-
-    auto out = std::make_shared<Storage>(dev, n, s);
-    launch("voxel_reduce_kernel", s, 24 * (size_t)n, [&] {
-        voxel_reduce_kernel<<<ntiles, VR_THREADS, 0, s>>>(sorted, (uint32_t)n, kp.idxbits, in->d_pts, scale, inv_scale, out->d_pts, ticket,
-                                                           reinterpret_cast<uint64_t *>(ab + off_status), reinterpret_cast<TileRecord *>(ab + off_records),
-                                                           reinterpret_cast<VoxelAgg *>(ab + off_head), reinterpret_cast<VoxelAgg *>(ab + off_tail), done, ntiles, d_total);
-    });
-    uint32_t *h = static_cast<uint32_t *>(thread_pinned(2 * sizeof(uint32_t)));
-    CWCU_CHECK(cudaMemcpyAsync(h, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaMemcpyAsync(h + 1, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
-    if (h[1] != 0) {
-        result.failed = true;
-        result.error = "point coordinates out of range for voxel size " + std::to_string(cellsize) + " (|x/voxelsize| must stay below 2^22)";
-        return result;
+    // hash table in the thread's zeroed workspace: [header | capacity slots], load factor <= 2/3
+    const size_t capacity = plan.capacity;
+    const int slotbits = plan.slotbits;
+    uint8_t *ws = static_cast<uint8_t *>(thread_zeroed(dev, sizeof(TableHeader) + capacity * sizeof(VoxelSlot), s));
+    TableHeader *header = reinterpret_cast<TableHeader *>(ws);
+    VoxelSlot *table = reinterpret_cast<VoxelSlot *>(ws + sizeof(TableHeader));
+    try {
+        Scratch list(n * sizeof(uint64_t), s);
+        launch("voxel_accumulate_kernel", s, 16 * (size_t)n, [&] {
+            voxel_accumulate_kernel<<<stream_grid(n, dev), VA_THREADS, 0, s>>>(in->d_pts, (uint32_t)n, kp, scale, table, (uint32_t)(capacity - 1), slotbits, list.as<uint64_t>(), header);
+        });
+        uint32_t *h = static_cast<uint32_t *>(thread_pinned(2 * sizeof(uint32_t)));
+        CWCU_CHECK(cudaMemcpyAsync(h, header, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        const size_t v = h[0];
+        if (h[1] != 0) {
+            thread_zeroed_invalidate(dev);
+            result.failed = true;
+            result.error = "point coordinates out of range for voxel size " + std::to_string(cellsize) + " (|x/voxelsize| must stay below 2^22)";
+            return result;
+        }
+        Scratch other(v * sizeof(uint64_t), s);
+        const uint64_t *sorted = radix_sort_u64(list.as<uint64_t>(), other.as<uint64_t>(), v, slotbits, slotbits + plan.keybits, dev, s);
+        auto out = std::make_shared<Storage>(dev, v, s);
+        launch("voxel_emit_kernel", s, 16 * v, [&] {
+            voxel_emit_kernel<<<(unsigned)std::max<size_t>(1, div_up(v, 256)), 256, 0, s>>>(sorted, (uint32_t)v, (uint32_t)(capacity - 1), table, inv_scale, out->d_pts, header);
+        });
+        out->count = v;
+        // centroids lie inside the input's bounding box: hand it on so that a following filter need not recompute it
+        out->has_bounds = true;
+        for (int a = 0; a < 3; a++) {
+            out->bounds_min[a] = plan.gmin[a];
+            out->bounds_max[a] = plan.gmax[a];
+        }
+        out->mark_ready();
+        result.out = out;
+    } catch (...) {
+        thread_zeroed_invalidate(dev);
+        throw;
     }
-    out->count = h[0];
-    profile_add_bytes("voxel_reduce_kernel", 16 * (size_t)h[0]); // voxels written
-    out->mark_ready();
-    result.out = out;
     return result;
 }
 

@@ -38,9 +38,25 @@ cwipc_pointcloud *unary_filter(const char *who, cwipc_pointcloud *pc, Body &&bod
     });
 }
 
+// a subset of a cloud lies inside any box that contains the cloud
+void inherit_bounds(Storage &out, const Storage &in) {
+    if (!in.has_bounds) return;
+    out.has_bounds = true;
+    memcpy(out.bounds_min, in.bounds_min, sizeof(out.bounds_min));
+    memcpy(out.bounds_max, in.bounds_max, sizeof(out.bounds_max));
+}
+
+const float *bounds_of(const Storage &in, float box[6]) {
+    if (!in.has_bounds) return nullptr;
+    memcpy(box, in.bounds_min, 3 * sizeof(float));
+    memcpy(box + 3, in.bounds_max, 3 * sizeof(float));
+    return box;
+}
+
 StoragePtr compact_to_new(const StoragePtr &in, const Predicate &pred, int dev, cudaStream_t s) {
     auto out = std::make_shared<Storage>(dev, in->count, s);
     out->count = compact_points(in->d_pts, in->count, out->d_pts, pred, dev, s);
+    inherit_bounds(*out, *in);
     out->mark_ready();
     return out;
 }
@@ -174,9 +190,12 @@ cwipc_pointcloud *cwipc_remove_outliers(cwipc_pointcloud *pc, int kNeighbors, fl
     return unary_filter("cwipc_remove_outliers", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
         const float spacing = pc->cellsize();
         const size_t n = in->count;
+        float box[6];
+        const float *bounds = bounds_of(*in, box);
         if (!perTile) {
             auto out = std::make_shared<Storage>(dev, n, s);
-            out->count = remove_outliers_points(in->d_pts, n, out->d_pts, kNeighbors, stddevMulThresh, spacing, dev, s);
+            out->count = remove_outliers_points(in->d_pts, n, out->d_pts, kNeighbors, stddevMulThresh, spacing, bounds, dev, s);
+            inherit_bounds(*out, *in);
             out->mark_ready();
             return out;
         }
@@ -195,9 +214,10 @@ cwipc_pointcloud *cwipc_remove_outliers(cwipc_pointcloud *pc, int kNeighbors, fl
                 cnt = compact_points(in->d_pts, n, group.as<cwipc_point>(), p, dev, s);
                 src = group.as<cwipc_point>();
             }
-            total += remove_outliers_points(src, cnt, out->d_pts + total, kNeighbors, stddevMulThresh, spacing, dev, s);
+            total += remove_outliers_points(src, cnt, out->d_pts + total, kNeighbors, stddevMulThresh, spacing, bounds, dev, s);
         }
         out->count = total;
+        inherit_bounds(*out, *in);
         out->mark_ready();
         return out;
     });
@@ -214,7 +234,8 @@ int cwipc_cuda_knn_mean_distances(cwipc_pointcloud *pc, int kNeighbors, float *d
         cudaStream_t s = thread_stream(in->dev);
         in->acquire_for_read(s);
         Scratch d(in->count * sizeof(float), s);
-        knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), d.as<float>(), in->dev, s);
+        float box[6];
+        knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), bounds_of(*in, box), d.as<float>(), in->dev, s);
         CWCU_CHECK(cudaMemcpyAsync(dist, d.p, in->count * sizeof(float), cudaMemcpyDeviceToHost, s));
         in->release_after_read(s);
         CWCU_CHECK(cudaStreamSynchronize(s));

@@ -44,9 +44,10 @@ void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_s
 // ---- outliers.cu ---------------------------------------------------------------------------
 // Statistical outlier removal on in[0..n) (one group).  Appends survivors to out (capacity >= n),
 // returns the number kept.  `hint_spacing` is the cloud's cellsize (0 if unknown).
-size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, int dev, cudaStream_t s);
+// `bounds` (min xyz, max xyz), when not null, is a box known to contain every point; it saves the bounding-box pass.
+size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, const float *bounds, int dev, cudaStream_t s);
 // First pass only: mean distance to the k nearest neighbours per point, original order, device array.
-void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, float *d_dist, int dev, cudaStream_t s);
+void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s);
 
 // ---- runtime.cu ----------------------------------------------------------------------------
 void flush_l2(int dev, cudaStream_t s);

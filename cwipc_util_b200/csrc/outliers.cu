@@ -667,13 +667,20 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
 
 } // namespace
 
-void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, float *d_dist, int dev, cudaStream_t s) {
+void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s) {
     if (n == 0) return;
     if (k < 1) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors must be >= 1"};
     if (k + 1 > 64) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > 63 is not supported by libcwipc_util_cuda"};
     if ((size_t)k >= n) throw CudaError{cudaErrorInvalidValue, "remove_outliers: needs more than kNeighbors points"};
     float gmin[3], gmax[3];
-    global_bbox(in, n, gmin, gmax, dev, s);
+    if (bounds) {
+        for (int a = 0; a < 3; a++) {
+            gmin[a] = bounds[a];
+            gmax[a] = bounds[3 + a];
+        }
+    } else {
+        global_bbox(in, n, gmin, gmax, dev, s);
+    }
     for (int a = 0; a < 3; a++)
         if (!std::isfinite(gmin[a]) || !std::isfinite(gmax[a])) throw CudaError{cudaErrorInvalidValue, "remove_outliers: pointcloud contains non-finite coordinates"};
     const GridPlan plan = choose_grid(gmin, gmax, n, k, hint_spacing);
@@ -707,7 +714,7 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     else go(std::integral_constant<int, 64>{});
 }
 
-size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, int dev, cudaStream_t s) {
+size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, const float *bounds, int dev, cudaStream_t s) {
     if (n == 0) return 0;
     if (k < 1 || (size_t)k >= n) {
         // n <= k is undefined behaviour in the reference (PCL reads k+1 results where FLANN returned fewer);
@@ -717,7 +724,7 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
         return n;
     }
     Scratch dist(n * sizeof(float), s);
-    knn_mean_distances(in, n, k, hint_spacing, dist.as<float>(), dev, s);
+    knn_mean_distances(in, n, k, hint_spacing, bounds, dist.as<float>(), dev, s);
 
     Scratch partial(2 * ST_BLOCKS * sizeof(double), s);
     launch("stats_kernel", s, 4 * (size_t)n, [&] { stats_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>()); });

@@ -25,6 +25,7 @@ struct DeviceState {
     int sm_count = 0;
     std::mutex mu;
     std::vector<cudaStream_t> idle_streams; // streams returned by exited threads
+    std::vector<std::pair<void *, size_t>> idle_zeroed; // workspaces returned by exited threads (contents unknown)
 };
 
 int g_ndev = -1;
@@ -68,6 +69,12 @@ struct ThreadState {
     std::vector<cudaStream_t> streams; // per device
     void *pinned = nullptr;
     size_t pinned_size = 0;
+    struct Zeroed {
+        void *p = nullptr;
+        size_t size = 0;
+        bool dirty = false;
+    };
+    std::vector<Zeroed> zeroed; // per device
     ~ThreadState() {
         // give streams back so that thread churn does not leak them
         if (g_devs) {
@@ -75,6 +82,14 @@ struct ThreadState {
                 if (streams[d]) {
                     std::lock_guard<std::mutex> lk(g_devs[d].mu);
                     g_devs[d].idle_streams.push_back(streams[d]);
+                }
+            }
+        }
+        if (g_devs) {
+            for (size_t d = 0; d < zeroed.size(); d++) {
+                if (zeroed[d].p) {
+                    std::lock_guard<std::mutex> lk(g_devs[d].mu);
+                    g_devs[d].idle_zeroed.emplace_back(zeroed[d].p, zeroed[d].size);
                 }
             }
         }
@@ -166,6 +181,46 @@ void *thread_pinned(size_t bytes) {
         t_state.pinned_size = bytes;
     }
     return t_state.pinned;
+}
+
+void *thread_zeroed(int dev, size_t bytes, cudaStream_t s) {
+    if ((int)t_state.zeroed.size() <= dev) t_state.zeroed.resize(dev + 1);
+    auto &z = t_state.zeroed[dev];
+    if (!z.p) { // adopt a workspace an exited thread left behind
+        DeviceState &st = g_devs[dev];
+        bool adopted = false;
+        {
+            std::lock_guard<std::mutex> lk(st.mu);
+            if (!st.idle_zeroed.empty()) {
+                z.p = st.idle_zeroed.back().first;
+                z.size = st.idle_zeroed.back().second;
+                z.dirty = true;
+                st.idle_zeroed.pop_back();
+                adopted = true;
+            }
+        }
+        // its previous owner's stream may still be draining: rare (thread start-up), so simply wait
+        if (adopted) CWCU_CHECK(cudaDeviceSynchronize());
+    }
+    if (z.size < bytes) {
+        if (z.p) dfree(z.p, s);
+        z.p = nullptr;
+        z.size = 0;
+        size_t want = 1;
+        while (want < bytes) want <<= 1;
+        z.p = dmalloc(want, s);
+        z.size = want;
+        z.dirty = true;
+    }
+    if (z.dirty) {
+        CWCU_CHECK(cudaMemsetAsync(z.p, 0, z.size, s));
+        z.dirty = false;
+    }
+    return z.p;
+}
+
+void thread_zeroed_invalidate(int dev) {
+    if ((int)t_state.zeroed.size() > dev) t_state.zeroed[dev].dirty = true;
 }
 
 bool is_pinned_host(const void *p) {

@@ -61,6 +61,12 @@ void dfree(void *p, cudaStream_t s) noexcept;
 // Small page-locked scratch owned by the calling thread (count readbacks etc.), >= bytes, 16B aligned.
 void *thread_pinned(size_t bytes);
 bool is_pinned_host(const void *p);
+// Device workspace owned by the calling thread (one per device), at least `bytes` long, that is ALL
+// ZERO when handed out and that the caller must leave all zero again (the kernel that consumes an
+// entry clears it), so that steady-state calls need no memset.  Work on it must be queued on `s`,
+// the thread's stream.  Call thread_zeroed_invalidate() when a failure may have left it dirty.
+void *thread_zeroed(int dev, size_t bytes, cudaStream_t s);
+void thread_zeroed_invalidate(int dev);
 
 // Scratch block freed (stream-ordered) at scope exit.
 struct Scratch {
@@ -95,6 +101,9 @@ struct Storage {
     cudaEvent_t ready = nullptr;
     std::mutex mu;
     std::vector<std::pair<cudaStream_t, cudaEvent_t>> readers; // latest read per foreign stream
+    // A box known to contain every point (not necessarily tight), when a producer had one for free.
+    bool has_bounds = false;
+    float bounds_min[3] = {0, 0, 0}, bounds_max[3] = {0, 0, 0};
 
     Storage(int dev, size_t capacity, cudaStream_t home);
     ~Storage();
