@@ -33,8 +33,6 @@ namespace cwcu {
 
 namespace {
 
-constexpr int BB_CHUNK = 1024;   // points per bounding-box chunk
-constexpr int BB_THREADS = 256;
 constexpr int WL_RADIX = 72;     // voxel-in-leaf coordinate range per axis (64 + misalignment + guard)
 constexpr int WL_BITS = 19;      // 72^3 = 373248 < 2^19
 constexpr int MAX_OCTREE_DEPTH = 14;
@@ -48,20 +46,17 @@ struct OctreeBox {
     int error; // 1: runaway growth (non-finite input)
 };
 
-// ---- per-chunk bounding boxes --------------------------------------------------------------
-__global__ void __launch_bounds__(BB_THREADS) chunk_bbox_kernel(const cwipc_point *__restrict__ pts, uint32_t n, float *__restrict__ chunk_bbox) {
-    __shared__ float s_red[6][BB_THREADS / 32];
-    const uint32_t base = blockIdx.x * BB_CHUNK;
+// ---- per-chunk bounding boxes (device function; the kernel follows the octree replay below) ------------
+constexpr int BB_CHUNK = 1024;   // points per bounding-box chunk == threads per block
+__device__ __forceinline__ void chunk_bbox_block(const cwipc_point *__restrict__ pts, uint32_t n, float *chunk_bbox) {
+    __shared__ float s_cb[6][BB_CHUNK / 32];
+    const uint32_t i = blockIdx.x * BB_CHUNK + threadIdx.x;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < BB_CHUNK / BB_THREADS; j++) {
-        const uint32_t i = base + j * BB_THREADS + threadIdx.x;
-        if (i < n) {
-            const Point16 p = ld_point_stream(pts, i);
-            lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
-            lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
-            lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
-        }
+    if (i < n) {
+        const Point16 p = ld_point_stream(pts, i);
+        lo[0] = hi[0] = p.x;
+        lo[1] = hi[1] = p.y;
+        lo[2] = hi[2] = p.z;
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -75,15 +70,15 @@ __global__ void __launch_bounds__(BB_THREADS) chunk_bbox_kernel(const cwipc_poin
     if (lane_id() == 0) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            s_red[a][warp] = lo[a];
-            s_red[3 + a][warp] = hi[a];
+            s_cb[a][warp] = lo[a];
+            s_cb[3 + a][warp] = hi[a];
         }
     }
     __syncthreads();
     if (threadIdx.x < 6) {
-        float v = s_red[threadIdx.x][0];
-        for (int w = 1; w < BB_THREADS / 32; w++) v = threadIdx.x < 3 ? fminf(v, s_red[threadIdx.x][w]) : fmaxf(v, s_red[threadIdx.x][w]);
-        chunk_bbox[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+        float v = s_cb[threadIdx.x][0];
+        for (int w = 1; w < BB_CHUNK / 32; w++) v = threadIdx.x < 3 ? fminf(v, s_cb[threadIdx.x][w]) : fmaxf(v, s_cb[threadIdx.x][w]);
+        __stcg(chunk_bbox + (size_t)blockIdx.x * 6 + threadIdx.x, v);
     }
 }
 
@@ -96,8 +91,8 @@ __device__ __forceinline__ bool violates(const double *mn, const double *mx, flo
     return (double)lx < mn[0] || (double)ly < mn[1] || (double)lz < mn[2] || (double)hx >= mx[0] || (double)hy >= mx[1] || (double)hz >= mx[2];
 }
 
-__global__ void __launch_bounds__(1024) octree_box_kernel(const cwipc_point *__restrict__ pts, uint32_t n, const float *__restrict__ chunk_bbox, uint32_t nchunks, double res,
-                                                           int do_octree, OctreeBox *__restrict__ out) {
+__device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__ pts, uint32_t n, const float *chunk_bbox, uint32_t nchunks, double res, int do_octree,
+                                                  OctreeBox *__restrict__ out) {
     __shared__ float s_red[6][32];
     __shared__ double s_min[3], s_max[3];
     __shared__ int s_depth, s_error;
@@ -109,8 +104,8 @@ __global__ void __launch_bounds__(1024) octree_box_kernel(const cwipc_point *__r
     for (uint32_t c = tid; c < nchunks; c += 1024) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            lo[a] = fminf(lo[a], chunk_bbox[(size_t)c * 6 + a]);
-            hi[a] = fmaxf(hi[a], chunk_bbox[(size_t)c * 6 + 3 + a]);
+            lo[a] = fminf(lo[a], __ldcg(chunk_bbox + (size_t)c * 6 + a));
+            hi[a] = fmaxf(hi[a], __ldcg(chunk_bbox + (size_t)c * 6 + 3 + a));
         }
     }
 #pragma unroll
@@ -166,7 +161,7 @@ __global__ void __launch_bounds__(1024) octree_box_kernel(const cwipc_point *__r
         // first chunk at or after the cursor whose box sticks out
         for (uint32_t c = cursor / BB_CHUNK + tid; c < nchunks; c += 1024) {
             const float *b = chunk_bbox + (size_t)c * 6;
-            if (violates(s_min, s_max, b[0], b[1], b[2], b[3], b[4], b[5])) {
+            if (violates(s_min, s_max, __ldcg(b), __ldcg(b + 1), __ldcg(b + 2), __ldcg(b + 3), __ldcg(b + 4), __ldcg(b + 5))) {
                 atomicMin(&s_first, c);
                 break;
             }
@@ -223,6 +218,25 @@ __global__ void __launch_bounds__(1024) octree_box_kernel(const cwipc_point *__r
         out->depth = s_depth;
         out->error = s_error;
     }
+}
+
+// One launch: every block boxes its 1024-point chunk; the block that finishes last reduces the chunk boxes
+// and replays the octree growth (the classic "last block" pattern: fence, ticket, fence).
+__global__ void __launch_bounds__(BB_CHUNK) bbox_octree_kernel(const cwipc_point *__restrict__ pts, uint32_t n, float *chunk_bbox, uint32_t nchunks, double res, int do_octree,
+                                                                uint32_t *__restrict__ done_counter, OctreeBox *__restrict__ out) {
+    __shared__ bool s_last;
+    chunk_bbox_block(pts, n, chunk_bbox);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(done_counter, 1u);
+        s_last = ticket == nchunks - 1;
+        if (s_last) *done_counter = 0; // leave the counter clean for the next call
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    octree_box_block(pts, n, chunk_bbox, nchunks, res, do_octree, out);
 }
 
 // ---- key generation --------------------------------------------------------------------------
@@ -448,6 +462,12 @@ int bit_length(uint64_t v) {
     return b;
 }
 
+// the "last block" ticket of bbox_octree_kernel: a word of the thread's zeroed workspace header (pad[0])
+uint32_t *bbox_counter(int dev, cudaStream_t s) {
+    TableHeader *h = static_cast<TableHeader *>(thread_zeroed(dev, sizeof(TableHeader), s));
+    return &h->pad[0];
+}
+
 struct Plan {
     KeyParams kp;
     int keybits = 0;
@@ -467,15 +487,13 @@ Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_spl
     Scratch box(sizeof(OctreeBox), s);
     const float octree_cellsize = 64 * cellsize;           // ref: src/cwipc_filters.cpp:113-114 (float)
     const double res = (double)octree_cellsize;
-    launch("chunk_bbox_kernel", s, 16 * (size_t)n, [&] { chunk_bbox_kernel<<<nchunks, BB_THREADS, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>()); });
-    launch("octree_box_kernel", s, 24 * (size_t)nchunks, [&] {
-        octree_box_kernel<<<1, 1024, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, box.as<OctreeBox>());
+    launch("bbox_octree_kernel", s, 16 * (size_t)n, [&] {
+        bbox_octree_kernel<<<nchunks, BB_CHUNK, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, bbox_counter(dev, s), box.as<OctreeBox>());
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
     const OctreeBox ob = *h;
-    (void)dev;
 
     KeyParams &kp = plan.kp;
     memset(&kp, 0, sizeof(kp));
@@ -622,12 +640,12 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
 }
 
 void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], int dev, cudaStream_t s) {
-    (void)dev;
     const uint32_t nchunks = (uint32_t)div_up(n, BB_CHUNK);
     Scratch chunk_bbox((size_t)nchunks * 6 * sizeof(float), s);
     Scratch box(sizeof(OctreeBox), s);
-    launch("chunk_bbox_kernel", s, 16 * (size_t)n, [&] { chunk_bbox_kernel<<<nchunks, BB_THREADS, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>()); });
-    launch("octree_box_kernel", s, 24 * (size_t)nchunks, [&] { octree_box_kernel<<<1, 1024, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, box.as<OctreeBox>()); });
+    launch("bbox_octree_kernel", s, 16 * (size_t)n, [&] {
+        bbox_octree_kernel<<<nchunks, BB_CHUNK, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, bbox_counter(dev, s), box.as<OctreeBox>());
+    });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));

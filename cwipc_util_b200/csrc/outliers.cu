@@ -9,9 +9,9 @@
 // The kd-tree is replaced by a uniform grid in Morton order with a dense table pyramid:
 //   knn_keygen_kernel   16 B read + 8 B   key = [Morton(cell) | point index]
 //   radix_sort_u64      P x (8+8) B       (shared with downsample)
-//   knn_gather_kernel   8+16 B read, 16 B points re-laid out in cell order: every cell, and every aligned
-//                                         2^l-cube of cells, is one contiguous range of the array
-//   cell_table_kernel   8 B read          dense (begin,end) table of every level, scattered from the
+//   knn_layout_kernel   8+16 B read, 16 B points re-laid out in cell order (every cell, and every aligned
+//                                         2^l-cube of cells, is one contiguous range of the array) and the
+//                                         dense (begin,end) table of every level, scattered from the
 //                                         positions where the Morton prefix changes
 //   knn_tile_kernel     one warp per 32 consecutive queries, one lane per query.  Candidates = the cells
 //                       within Rc cell pitches of the queries' bounding box, streamed into shared memory
@@ -97,19 +97,18 @@ __global__ void __launch_bounds__(256) knn_keygen_kernel(const cwipc_point *__re
     }
 }
 
-__global__ void __launch_bounds__(256) knn_gather_kernel(const uint64_t *__restrict__ sorted, uint32_t n, int idxbits, const cwipc_point *__restrict__ pts,
-                                                          cwipc_point *__restrict__ spts) {
-    const uint64_t idxmask = (1ull << idxbits) - 1ull;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) st_point(spts, j, ld_point(pts, (size_t)(sorted[j] & idxmask)));
-}
-
-// ---- table pyramid: (begin, end) of every node of every level ----------------------------------------
-// Position i starts a new level-l node iff the Morton codes of i-1 and i differ above bit 3l.  The
-// thread at such a position writes `begin` of the node it opens and `end` of the node it closes, for
-// every level at which it is a boundary; empty nodes keep the (0,0) of the memset.
-__global__ void __launch_bounds__(256) cell_table_kernel(const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, uint2 *__restrict__ table) {
+// ---- cell-ordered layout + table pyramid in one pass over the sorted keys ------------------------------
+// (a) points are re-laid out in cell order; (b) (begin, end) of every node of every level: position i
+// starts a new level-l node iff the Morton codes of i-1 and i differ above bit 3l.  The thread at such
+// a position writes `begin` of the node it opens and `end` of the node it closes, for every level at
+// which it is a boundary; empty nodes keep the (0,0) of the memset.
+__global__ void __launch_bounds__(256) knn_layout_kernel(const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, const cwipc_point *__restrict__ pts,
+                                                          cwipc_point *__restrict__ spts, uint2 *__restrict__ table) {
+    const uint64_t idxmask = (1ull << gp.idxbits) - 1ull;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint64_t code = sorted[i] >> gp.idxbits;
+        const uint64_t word = sorted[i];
+        st_point(spts, i, ld_point(pts, (size_t)(word & idxmask)));
+        const uint64_t code = word >> gp.idxbits;
         int top; // highest level at which position i opens a node
         uint64_t prev = 0;
         if (i == 0) {
@@ -296,20 +295,25 @@ __global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point 
                 const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1, nbz = cz1 - cz0 + 1;
                 const int nb = nbx * nby * nbz; // <= 8*8*8: the queries span at most 4 cells per axis and rc <= 1.5
                 const float rc2 = rc * rc;
-                for (int t0 = 0; t0 < nb; t0 += 32) {
-                    const int t = t0 + (int)lane;
-                    uint2 r = make_uint2(0u, 0u);
-                    if (t < nb) {
-                        const int ix = cx0 + t % nbx, iy = cy0 + (t / nbx) % nby, iz = cz0 + t / (nbx * nby);
-                        const float dx = fmaxf(fmaxf((float)ix - hix, lox - (float)(ix + 1)), 0.f);
-                        const float dy = fmaxf(fmaxf((float)iy - hiy, loy - (float)(iy + 1)), 0.f);
-                        const float dz = fmaxf(fmaxf((float)iz - hiz, loz - (float)(iz + 1)), 0.f);
-                        if (dx * dx + dy * dy + dz * dz <= rc2) r = table[table_index(gp, 0, (uint32_t)ix, (uint32_t)iy, (uint32_t)iz)];
+                // cells that overlap the queries' box first: their points tighten the running bound early,
+                // so most candidates of the surrounding shell fail the threshold test without being parked
+                for (int shell = 0; shell < 2; shell++) {
+                    for (int t0 = 0; t0 < nb; t0 += 32) {
+                        const int t = t0 + (int)lane;
+                        uint2 r = make_uint2(0u, 0u);
+                        if (t < nb) {
+                            const int ix = cx0 + t % nbx, iy = cy0 + (t / nbx) % nby, iz = cz0 + t / (nbx * nby);
+                            const float dx = fmaxf(fmaxf((float)ix - hix, lox - (float)(ix + 1)), 0.f);
+                            const float dy = fmaxf(fmaxf((float)iy - hiy, loy - (float)(iy + 1)), 0.f);
+                            const float dz = fmaxf(fmaxf((float)iz - hiz, loz - (float)(iz + 1)), 0.f);
+                            const float dd = dx * dx + dy * dy + dz * dz;
+                            if (shell == 0 ? dd == 0.f : (dd > 0.f && dd <= rc2)) r = table[table_index(gp, 0, (uint32_t)ix, (uint32_t)iy, (uint32_t)iz)];
+                        }
+                        const unsigned has = __ballot_sync(FULL_MASK, r.y > r.x);
+                        if (r.y > r.x) ws.ranges[nr + __popc(has & lt)] = r;
+                        nr += __popc(has);
+                        total += warp_sum(r.y - r.x);
                     }
-                    const unsigned has = __ballot_sync(FULL_MASK, r.y > r.x);
-                    if (r.y > r.x) ws.ranges[nr + __popc(has & lt)] = r;
-                    nr += __popc(has);
-                    total += warp_sum(r.y - r.x);
                 }
             }
             __syncwarp();
@@ -479,7 +483,20 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
                     float d2 = INFINITY;
                     if (c < node.pe) d2 = dist2(q, spts16[c]);
                     const bool pass = d2 < tau && d2 <= limit;
-                    if (!__any_sync(FULL_MASK, pass)) continue;
+                    unsigned pm = __ballot_sync(FULL_MASK, pass);
+                    if (pm == 0u) continue;
+                    if (KPL == 1 && __popc(pm) <= 6) {
+                        // few survivors: insert them one by one into the lane-distributed sorted list
+                        while (pm) {
+                            const int src = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            const float x = __shfl_sync(FULL_MASK, d2, src);
+                            const float up = __shfl_up_sync(FULL_MASK, v[0], 1);
+                            if (v[0] > x) v[0] = (lane == 0) ? x : fmaxf(up, x);
+                        }
+                        tau = __shfl_sync(FULL_MASK, v[0], (kk - 1) & 31);
+                        continue;
+                    }
                     const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
                     const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
                     if (KPL == 1) {
@@ -693,14 +710,14 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] { knn_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in, (uint32_t)n, gp, keys_a.as<uint64_t>()); });
     const uint64_t *sorted = radix_sort_u64(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), n, gp.idxbits, gp.idxbits + keybits, dev, s);
 
+    // cell-ordered points, table pyramid, far-query counter
     Scratch spts(n * sizeof(cwipc_point), s);
-    launch("knn_gather_kernel", s, 40 * (size_t)n, [&] { knn_gather_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, in, spts.as<cwipc_point>()); });
-
-    // table pyramid + far-query counter
     Scratch table(plan.table_entries * sizeof(uint2) + 16, s);
     CWCU_CHECK(cudaMemsetAsync(table.p, 0, plan.table_entries * sizeof(uint2) + 16, s));
     uint32_t *far_count = reinterpret_cast<uint32_t *>(table.as<uint2>() + plan.table_entries);
-    launch("cell_table_kernel", s, 8 * (size_t)n, [&] { cell_table_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp, table.as<uint2>()); });
+    launch("knn_layout_kernel", s, 48 * (size_t)n, [&] {
+        knn_layout_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp, in, spts.as<cwipc_point>(), table.as<uint2>());
+    });
 
     // a query is queued at most once
     Scratch far_list((n + 64) * sizeof(FarEntry), s);

@@ -10,6 +10,9 @@
 // HBM-bound: per pass 8 B read + 8 B written per key (+ 8 B per key once for the histograms).
 #include "radix_sort.hpp"
 
+#include <cooperative_groups.h>
+#include <mutex>
+
 #include "device_utils.cuh"
 
 namespace cwcu {
@@ -192,6 +195,136 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const uint64
     }
 }
 
+// ---- small inputs: every pass in ONE cooperative launch ------------------------------------------------
+// Up to one 4096-key tile per co-resident block.  Per pass: rank the tile (same warp match_any ranking
+// as above), publish its 256 digit counts, grid barrier, every block sums the counts of the tiles
+// before it and of all tiles (no look-back chain, no per-pass launch), scatter, grid barrier.  A sort
+// of a few hundred thousand keys is launch- and latency-bound; this removes 2 + P launches.
+__global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__restrict__ a, uint64_t *__restrict__ b, uint32_t n, int begin_bit, int end_bit,
+                                                                  uint32_t *__restrict__ tile_hist /* [2][ntiles][256] */) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_BINS];
+    __shared__ uint32_t s_bin_excl[RS_BINS];
+    __shared__ uint32_t s_bin_out[RS_BINS];
+    __shared__ uint32_t s_scan[RS_WARPS];
+    __shared__ uint64_t s_keys[RS_TILE];
+
+    const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
+    const uint32_t tile_base = tile * RS_TILE;
+    const uint32_t tile_count = tile_base < n ? min((uint32_t)RS_TILE, n - tile_base) : 0u;
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t warp_base = tile_base + warp * (32 * RS_ITEMS);
+    const uint32_t d = threadIdx.x;
+    uint64_t *src = a, *dst = b;
+    int pass = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8, pass++) {
+        const int bits = min(8, end_bit - shift);
+        const uint32_t mask = (1u << bits) - 1u;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) s_warp_hist[w][threadIdx.x] = 0;
+        __syncthreads();
+
+        uint64_t key[RS_ITEMS];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t idx = warp_base + i * 32 + lane;
+            key[i] = idx < n ? src[idx] : ~0ull;
+        }
+        uint32_t rank[RS_ITEMS];
+        uint32_t *my_hist = s_warp_hist[warp];
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t idx = warp_base + i * 32 + lane;
+            const bool valid = idx < n;
+            const uint32_t dg = valid ? digit_of(key[i], shift, mask) : 0x100u;
+            const unsigned peers = __match_any_sync(FULL_MASK, dg);
+            const int leader = __ffs(peers) - 1;
+            uint32_t before = 0;
+            if ((int)lane == leader && valid) {
+                before = my_hist[dg];
+                my_hist[dg] = before + __popc(peers);
+            }
+            before = __shfl_sync(FULL_MASK, before, leader);
+            rank[i] = before + __popc(peers & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        uint32_t count = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            const uint32_t c = s_warp_hist[w][d];
+            s_warp_hist[w][d] = count;
+            count += c;
+        }
+        uint32_t *hist = tile_hist + (size_t)(pass & 1) * ntiles * RS_BINS;
+        hist[(size_t)tile * RS_BINS + d] = count;
+        grid.sync();
+
+        // digit d: keys in earlier tiles, keys in all tiles
+        uint32_t before_tiles = 0, total = 0;
+        for (uint32_t t = 0; t < ntiles; t++) {
+            const uint32_t c = hist[(size_t)t * RS_BINS + d];
+            if (t < tile) before_tiles += c;
+            total += c;
+        }
+        {
+            // block-wide exclusive scans: of the totals (global digit base) and of the tile counts (staging layout)
+            const uint32_t incl_total = warp_inclusive_scan(total);
+            const uint32_t incl_count = warp_inclusive_scan(count);
+            if (lane == 31) s_scan[warp] = incl_total;
+            __syncthreads();
+            uint32_t off_total = 0;
+            for (int w = 0; w < (int)warp; w++) off_total += s_scan[w];
+            __syncthreads();
+            if (lane == 31) s_scan[warp] = incl_count;
+            __syncthreads();
+            uint32_t off_count = 0;
+            for (int w = 0; w < (int)warp; w++) off_count += s_scan[w];
+            const uint32_t digit_base = off_total + incl_total - total;
+            const uint32_t excl_in_tile = off_count + incl_count - count;
+            s_bin_excl[d] = excl_in_tile;
+            s_bin_out[d] = digit_base + before_tiles - excl_in_tile;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t idx = warp_base + i * 32 + lane;
+            if (idx < n) {
+                const uint32_t dd = digit_of(key[i], shift, mask);
+                s_keys[s_bin_excl[dd] + my_hist[dd] + rank[i]] = key[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; j++) {
+            const uint32_t p = j * RS_THREADS + threadIdx.x;
+            if (p < tile_count) {
+                const uint64_t k = s_keys[p];
+                dst[s_bin_out[digit_of(k, shift, mask)] + p] = k;
+            }
+        }
+        grid.sync();
+        uint64_t *t = src;
+        src = dst;
+        dst = t;
+    }
+}
+
+int fused_tile_limit(int dev) {
+    static int limit[64];
+    static std::once_flag once[64];
+    std::call_once(once[dev & 63], [&] {
+        int per_sm = 0, coop = 0;
+        CWCU_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        CWCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_fused_kernel, RS_THREADS, 0));
+        limit[dev & 63] = (coop && per_sm > 0) ? sm_count(dev) : 0; // one tile per SM keeps the barriers cheap
+    });
+    return limit[dev & 63];
+}
+
 } // namespace
 
 uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int end_bit, int dev, cudaStream_t s) {
@@ -200,6 +333,17 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
     const int npasses = (end_bit - begin_bit + 7) / 8;
     if (npasses > RS_MAX_PASSES) throw CudaError{cudaErrorInvalidValue, "radix_sort_u64: bit range too wide"};
     const size_t ntiles = div_up(n, RS_TILE);
+
+    if ((int)ntiles <= fused_tile_limit(dev)) {
+        Scratch hist(2 * ntiles * RS_BINS * sizeof(uint32_t), s);
+        uint32_t *tile_hist = hist.as<uint32_t>();
+        uint32_t n32 = (uint32_t)n;
+        void *args[] = {&a, &b, &n32, &begin_bit, &end_bit, &tile_hist};
+        launch("radix_fused_kernel", s, 16 * (size_t)n * npasses, [&] {
+            CWCU_CHECK(cudaLaunchCooperativeKernel((const void *)radix_fused_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, s));
+        });
+        return (npasses & 1) ? b : a;
+    }
 
     // [hist P*256 | binbase P*256 | tickets 8 | status P*ntiles*256] (u32 each)
     const size_t hist_words = (size_t)npasses * RS_BINS;
