@@ -130,6 +130,13 @@ class Worker(threading.Thread):
         self.d2h_bytes = 0
 
     def frame_chain(self, pc):
+        stage = os.environ.get("BENCH_STAGE", "")   # diagnostic only: time one stage of the chain
+        if stage == "downsample":
+            d = self.cw.cwipc_downsample(pc, VOXEL)
+            self.mid_points += d.count()
+            return d
+        if stage == "outliers":
+            return self.cw.cwipc_remove_outliers(self.state["mid_frames"][self.state["device_frames"].index(pc)], K, STDDEV, False)
         d = self.cw.cwipc_downsample(pc, VOXEL)
         o = self.cw.cwipc_remove_outliers(d, K, STDDEV, False)
         self.mid_points += d.count()
@@ -282,9 +289,13 @@ def run_ours(args):
         hp = lib.cwipc_cuda_host_alloc(POINTS_PER_FRAME * 16)
         ctypes.memmove(hp, pts.ctypes.data, POINTS_PER_FRAME * 16)
         host_ptrs.append(hp)
+    if os.environ.get("BENCH_STAGE", "") == "outliers":
+        state_mid = [cw.cwipc_downsample(pc, VOXEL) for pc in device_frames]
+    else:
+        state_mid = []
     nworkers = args.workers
     host_out = [lib.cwipc_cuda_host_alloc(POINTS_PER_FRAME * 16) for _ in range(nworkers)]
-    state = {"frames": frames, "device_frames": device_frames, "host_ptrs": host_ptrs, "host_out": host_out, "cellsize": cellsize, "stop": False, "mode": "resident"}
+    state = {"frames": frames, "device_frames": device_frames, "host_ptrs": host_ptrs, "host_out": host_out, "cellsize": cellsize, "stop": False, "mode": "resident", "mid_frames": state_mid}
     barrier = threading.Barrier(nworkers + 1)
     workers = [Worker(w, nworkers, dev, cw, lib, barrier, state) for w in range(nworkers)]
     for w in workers:

@@ -47,16 +47,21 @@ struct OctreeBox {
 };
 
 // ---- per-chunk bounding boxes (device function; the kernel follows the octree replay below) ------------
-constexpr int BB_CHUNK = 1024;   // points per bounding-box chunk == threads per block
+constexpr int BB_THREADS = 1024;
+constexpr int BB_ITEMS = 4;
+constexpr int BB_CHUNK = BB_THREADS * BB_ITEMS; // points per bounding-box chunk (one block)
 __device__ __forceinline__ void chunk_bbox_block(const cwipc_point *__restrict__ pts, uint32_t n, float *chunk_bbox) {
-    __shared__ float s_cb[6][BB_CHUNK / 32];
-    const uint32_t i = blockIdx.x * BB_CHUNK + threadIdx.x;
+    __shared__ float s_cb[6][BB_THREADS / 32];
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (i < n) {
-        const Point16 p = ld_point_stream(pts, i);
-        lo[0] = hi[0] = p.x;
-        lo[1] = hi[1] = p.y;
-        lo[2] = hi[2] = p.z;
+#pragma unroll
+    for (int j = 0; j < BB_ITEMS; j++) {
+        const uint32_t i = blockIdx.x * BB_CHUNK + j * BB_THREADS + threadIdx.x;
+        if (i < n) {
+            const Point16 p = ld_point_stream(pts, i);
+            lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+            lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+            lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+        }
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -77,7 +82,7 @@ __device__ __forceinline__ void chunk_bbox_block(const cwipc_point *__restrict__
     __syncthreads();
     if (threadIdx.x < 6) {
         float v = s_cb[threadIdx.x][0];
-        for (int w = 1; w < BB_CHUNK / 32; w++) v = threadIdx.x < 3 ? fminf(v, s_cb[threadIdx.x][w]) : fmaxf(v, s_cb[threadIdx.x][w]);
+        for (int w = 1; w < BB_THREADS / 32; w++) v = threadIdx.x < 3 ? fminf(v, s_cb[threadIdx.x][w]) : fmaxf(v, s_cb[threadIdx.x][w]);
         __stcg(chunk_bbox + (size_t)blockIdx.x * 6 + threadIdx.x, v);
     }
 }
@@ -101,7 +106,7 @@ __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__
 
     // global bounding box
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (uint32_t c = tid; c < nchunks; c += 1024) {
+    for (uint32_t c = tid; c < nchunks; c += BB_THREADS) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             lo[a] = fminf(lo[a], __ldcg(chunk_bbox + (size_t)c * 6 + a));
@@ -159,7 +164,7 @@ __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__
         __syncthreads();
         const uint32_t cursor = s_cursor;
         // first chunk at or after the cursor whose box sticks out
-        for (uint32_t c = cursor / BB_CHUNK + tid; c < nchunks; c += 1024) {
+        for (uint32_t c = cursor / BB_CHUNK + tid; c < nchunks; c += BB_THREADS) {
             const float *b = chunk_bbox + (size_t)c * 6;
             if (violates(s_min, s_max, __ldcg(b), __ldcg(b + 1), __ldcg(b + 2), __ldcg(b + 3), __ldcg(b + 4), __ldcg(b + 5))) {
                 atomicMin(&s_first, c);
@@ -172,11 +177,14 @@ __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__
         __syncthreads();
         if (tid == 0) s_first = 0xffffffffu;
         __syncthreads();
-        // first violating point of that chunk, not before the cursor (BB_CHUNK == blockDim.x)
-        const uint32_t i = cstar * BB_CHUNK + tid;
-        if (i >= cursor && i < n) {
-            const Point16 p = ld_point(pts, i);
-            if (violates(s_min, s_max, p.x, p.y, p.z, p.x, p.y, p.z)) atomicMin(&s_first, i);
+        // first violating point of that chunk, not before the cursor
+#pragma unroll
+        for (int j = 0; j < BB_ITEMS; j++) {
+            const uint32_t i = cstar * BB_CHUNK + j * BB_THREADS + tid;
+            if (i >= cursor && i < n) {
+                const Point16 p = ld_point(pts, i);
+                if (violates(s_min, s_max, p.x, p.y, p.z, p.x, p.y, p.z)) atomicMin(&s_first, i);
+            }
         }
         __syncthreads();
         const uint32_t istar = s_first;
@@ -222,7 +230,7 @@ __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__
 
 // One launch: every block boxes its 1024-point chunk; the block that finishes last reduces the chunk boxes
 // and replays the octree growth (the classic "last block" pattern: fence, ticket, fence).
-__global__ void __launch_bounds__(BB_CHUNK) bbox_octree_kernel(const cwipc_point *__restrict__ pts, uint32_t n, float *chunk_bbox, uint32_t nchunks, double res, int do_octree,
+__global__ void __launch_bounds__(BB_THREADS) bbox_octree_kernel(const cwipc_point *__restrict__ pts, uint32_t n, float *chunk_bbox, uint32_t nchunks, double res, int do_octree,
                                                                 uint32_t *__restrict__ done_counter, OctreeBox *__restrict__ out) {
     __shared__ bool s_last;
     chunk_bbox_block(pts, n, chunk_bbox);
@@ -389,15 +397,17 @@ __global__ void __launch_bounds__(VA_THREADS) voxel_accumulate_kernel(const cwip
             }
         }
         const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        bool claimed = false;
+        uint32_t slot = 0;
         if (valid && tail) {
             const unsigned long long want = key + 1ull;
-            uint32_t slot = hash_key(key) & slot_mask;
+            slot = hash_key(key) & slot_mask;
             while (true) {
                 unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&table[slot].keyp1);
                 if (cur == 0ull) {
                     cur = atomicCAS(&table[slot].keyp1, 0ull, want);
                     if (cur == 0ull) { // claimed: one list entry per voxel
-                        list[atomicAdd(&header->count, 1u)] = (key << slotbits) | slot;
+                        claimed = true;
                         break;
                     }
                 }
@@ -411,6 +421,14 @@ __global__ void __launch_bounds__(VA_THREADS) voxel_accumulate_kernel(const cwip
             atomicAdd(&sl->rg, rg);
             atomicAdd(&sl->bn, bn);
             atomicOr(&sl->tile, tl);
+        }
+        // one counter update per warp for the slots it claimed
+        const unsigned cm = __ballot_sync(FULL_MASK, claimed);
+        if (cm) {
+            uint32_t first = 0;
+            if (lane == (unsigned)(__ffs(cm) - 1)) first = atomicAdd(&header->count, (uint32_t)__popc(cm));
+            first = __shfl_sync(FULL_MASK, first, __ffs(cm) - 1);
+            if (claimed) list[first + __popc(cm & lanemask_lt())] = (key << slotbits) | slot;
         }
     }
     if (bad) atomicOr(&header->error, 1u);
@@ -488,7 +506,7 @@ Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_spl
     const float octree_cellsize = 64 * cellsize;           // ref: src/cwipc_filters.cpp:113-114 (float)
     const double res = (double)octree_cellsize;
     launch("bbox_octree_kernel", s, 16 * (size_t)n, [&] {
-        bbox_octree_kernel<<<nchunks, BB_CHUNK, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, bbox_counter(dev, s), box.as<OctreeBox>());
+        bbox_octree_kernel<<<nchunks, BB_THREADS, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, bbox_counter(dev, s), box.as<OctreeBox>());
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
@@ -644,7 +662,7 @@ void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], 
     Scratch chunk_bbox((size_t)nchunks * 6 * sizeof(float), s);
     Scratch box(sizeof(OctreeBox), s);
     launch("bbox_octree_kernel", s, 16 * (size_t)n, [&] {
-        bbox_octree_kernel<<<nchunks, BB_CHUNK, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, bbox_counter(dev, s), box.as<OctreeBox>());
+        bbox_octree_kernel<<<nchunks, BB_THREADS, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, bbox_counter(dev, s), box.as<OctreeBox>());
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));

@@ -446,7 +446,7 @@ __device__ __forceinline__ float warp_bitonic_merge32(float x, unsigned lane) { 
 template <int KPL>
 __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, const FarEntry *__restrict__ far_list,
-                                                              const uint32_t *__restrict__ far_count) {
+                                                              const uint32_t *__restrict__ far_count, uint32_t leaf_points) {
     __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     FarNode *stack = s_stack[warp];
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
             __syncwarp();
             const float thr = fminf(tau, limit);
             if (node.mind2 * 0.9999f > thr) continue;
-            if (node.level == 0 || node.pe - node.pb <= 64u) {
+            if (node.level == 0 || node.pe - node.pb <= leaf_points) {
                 for (uint32_t base = node.pb; base < node.pe; base += 32) {
                     const uint32_t c = base + lane;
                     float d2 = INFINITY;
@@ -677,8 +677,10 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     });
     if (gp.top_level == 0) return; // one cell spans the cloud: the main pass is exact for every query
     constexpr int KPL = KCAP > 32 ? 2 : 1;
+    // nodes with at most this many points are scanned directly instead of being expanded
+    static const uint32_t leaf_points = (uint32_t)env_float("CWIPC_CUDA_KNN_LEAF", 128.f, 1.f, 65536.f);
     launch("knn_far_kernel", s, (size_t)0, [&] {
-        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 4, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, far_list, far_count);
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 4, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, far_list, far_count, leaf_points);
     });
 }
 

@@ -200,15 +200,25 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const uint64
 // as above), publish its 256 digit counts, grid barrier, every block sums the counts of the tiles
 // before it and of all tiles (no look-back chain, no per-pass launch), scatter, grid barrier.  A sort
 // of a few hundred thousand keys is launch- and latency-bound; this removes 2 + P launches.
+constexpr int RF_BITS = 9;                 // digit width of the fused path (per-warp histograms: 8 x 512 x 4 B)
+constexpr int RF_BINS = 1 << RF_BITS;
+constexpr int RF_DPT = RF_BINS / RS_THREADS; // digits per thread (contiguous)
+
+constexpr size_t RF_SMEM_BYTES = RS_TILE * sizeof(uint64_t) + (size_t)(RS_WARPS + 2) * RF_BINS * sizeof(uint32_t) + 2 * RS_WARPS * sizeof(uint32_t);
+
+// pass widths: as few passes as RF_BITS allows, evenly wide
+__host__ __device__ __forceinline__ int fused_passes(int bits) { return (bits + RF_BITS - 1) / RF_BITS; }
+
 __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__restrict__ a, uint64_t *__restrict__ b, uint32_t n, int begin_bit, int end_bit,
-                                                                  uint32_t *__restrict__ tile_hist /* [2][ntiles][256] */) {
+                                                                  uint32_t *__restrict__ tile_hist /* [2][ntiles][RF_BINS] */) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    __shared__ uint32_t s_warp_hist[RS_WARPS][RS_BINS];
-    __shared__ uint32_t s_bin_excl[RS_BINS];
-    __shared__ uint32_t s_bin_out[RS_BINS];
-    __shared__ uint32_t s_scan[RS_WARPS];
-    __shared__ uint64_t s_keys[RS_TILE];
+    extern __shared__ __align__(16) unsigned char rf_smem[]; // RF_SMEM_BYTES, above the 48 KB static limit
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(rf_smem);                               // [RS_TILE]
+    uint32_t(*s_warp_hist)[RF_BINS] = reinterpret_cast<uint32_t(*)[RF_BINS]>(s_keys + RS_TILE); // [RS_WARPS][RF_BINS]
+    uint32_t *s_bin_excl = &s_warp_hist[RS_WARPS][0];                                       // [RF_BINS]
+    uint32_t *s_bin_out = s_bin_excl + RF_BINS;                                             // [RF_BINS]
+    uint32_t(*s_scan)[RS_WARPS] = reinterpret_cast<uint32_t(*)[RS_WARPS]>(s_bin_out + RF_BINS); // [2][RS_WARPS]
 
     const uint32_t tile = blockIdx.x, ntiles = gridDim.x;
     const uint32_t tile_base = tile * RS_TILE;
@@ -216,14 +226,16 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     const unsigned lt = lanemask_lt();
     const uint32_t warp_base = tile_base + warp * (32 * RS_ITEMS);
-    const uint32_t d = threadIdx.x;
     uint64_t *src = a, *dst = b;
-    int pass = 0;
-    for (int shift = begin_bit; shift < end_bit; shift += 8, pass++) {
-        const int bits = min(8, end_bit - shift);
+    const int npasses = fused_passes(end_bit - begin_bit);
+    int shift = begin_bit;
+    for (int pass = 0; pass < npasses; pass++) {
+        const int bits = (end_bit - shift + (npasses - pass) - 1) / (npasses - pass);
         const uint32_t mask = (1u << bits) - 1u;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) s_warp_hist[w][threadIdx.x] = 0;
+        for (int w = 0; w < RS_WARPS; w++)
+#pragma unroll
+            for (int j = 0; j < RF_DPT; j++) s_warp_hist[w][threadIdx.x * RF_DPT + j] = 0;
         __syncthreads();
 
         uint64_t key[RS_ITEMS];
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
         for (int i = 0; i < RS_ITEMS; i++) {
             const uint32_t idx = warp_base + i * 32 + lane;
             const bool valid = idx < n;
-            const uint32_t dg = valid ? digit_of(key[i], shift, mask) : 0x100u;
+            const uint32_t dg = valid ? digit_of(key[i], shift, mask) : 0xffffu;
             const unsigned peers = __match_any_sync(FULL_MASK, dg);
             const int leader = __ffs(peers) - 1;
             uint32_t before = 0;
@@ -252,41 +264,64 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
         }
         __syncthreads();
 
-        uint32_t count = 0;
+        // my RF_DPT digits: offsets across warps, tile counts
+        uint32_t count[RF_DPT];
+        uint32_t *hist = tile_hist + (size_t)(pass & 1) * ntiles * RF_BINS;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; w++) {
-            const uint32_t c = s_warp_hist[w][d];
-            s_warp_hist[w][d] = count;
-            count += c;
+        for (int j = 0; j < RF_DPT; j++) {
+            const uint32_t d = threadIdx.x * RF_DPT + j;
+            uint32_t c = 0;
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; w++) {
+                const uint32_t v = s_warp_hist[w][d];
+                s_warp_hist[w][d] = c;
+                c += v;
+            }
+            count[j] = c;
+            hist[(size_t)tile * RF_BINS + d] = c;
         }
-        uint32_t *hist = tile_hist + (size_t)(pass & 1) * ntiles * RS_BINS;
-        hist[(size_t)tile * RS_BINS + d] = count;
         grid.sync();
 
-        // digit d: keys in earlier tiles, keys in all tiles
-        uint32_t before_tiles = 0, total = 0;
+        // keys with my digits in earlier tiles and in all tiles
+        uint32_t before_tiles[RF_DPT], total[RF_DPT];
+#pragma unroll
+        for (int j = 0; j < RF_DPT; j++) before_tiles[j] = total[j] = 0;
         for (uint32_t t = 0; t < ntiles; t++) {
-            const uint32_t c = hist[(size_t)t * RS_BINS + d];
-            if (t < tile) before_tiles += c;
-            total += c;
+#pragma unroll
+            for (int j = 0; j < RF_DPT; j++) {
+                const uint32_t c = hist[(size_t)t * RF_BINS + threadIdx.x * RF_DPT + j];
+                if (t < tile) before_tiles[j] += c;
+                total[j] += c;
+            }
         }
         {
-            // block-wide exclusive scans: of the totals (global digit base) and of the tile counts (staging layout)
-            const uint32_t incl_total = warp_inclusive_scan(total);
-            const uint32_t incl_count = warp_inclusive_scan(count);
-            if (lane == 31) s_scan[warp] = incl_total;
+            // block-wide exclusive scans over the digits: totals (global digit base), tile counts (staging layout)
+            uint32_t sum_total = 0, sum_count = 0;
+#pragma unroll
+            for (int j = 0; j < RF_DPT; j++) {
+                sum_total += total[j];
+                sum_count += count[j];
+            }
+            const uint32_t incl_total = warp_inclusive_scan(sum_total);
+            const uint32_t incl_count = warp_inclusive_scan(sum_count);
+            if (lane == 31) {
+                s_scan[0][warp] = incl_total;
+                s_scan[1][warp] = incl_count;
+            }
             __syncthreads();
-            uint32_t off_total = 0;
-            for (int w = 0; w < (int)warp; w++) off_total += s_scan[w];
-            __syncthreads();
-            if (lane == 31) s_scan[warp] = incl_count;
-            __syncthreads();
-            uint32_t off_count = 0;
-            for (int w = 0; w < (int)warp; w++) off_count += s_scan[w];
-            const uint32_t digit_base = off_total + incl_total - total;
-            const uint32_t excl_in_tile = off_count + incl_count - count;
-            s_bin_excl[d] = excl_in_tile;
-            s_bin_out[d] = digit_base + before_tiles - excl_in_tile;
+            uint32_t run_total = incl_total - sum_total, run_count = incl_count - sum_count;
+            for (int w = 0; w < (int)warp; w++) {
+                run_total += s_scan[0][w];
+                run_count += s_scan[1][w];
+            }
+#pragma unroll
+            for (int j = 0; j < RF_DPT; j++) {
+                const uint32_t d = threadIdx.x * RF_DPT + j;
+                s_bin_excl[d] = run_count;
+                s_bin_out[d] = run_total + before_tiles[j] - run_count;
+                run_total += total[j];
+                run_count += count[j];
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -310,6 +345,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
         uint64_t *t = src;
         src = dst;
         dst = t;
+        shift += bits;
     }
 }
 
@@ -319,7 +355,8 @@ int fused_tile_limit(int dev) {
     std::call_once(once[dev & 63], [&] {
         int per_sm = 0, coop = 0;
         CWCU_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        CWCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_fused_kernel, RS_THREADS, 0));
+        CWCU_CHECK(cudaFuncSetAttribute(radix_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM_BYTES));
+        CWCU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_fused_kernel, RS_THREADS, RF_SMEM_BYTES));
         limit[dev & 63] = (coop && per_sm > 0) ? sm_count(dev) : 0; // one tile per SM keeps the barriers cheap
     });
     return limit[dev & 63];
@@ -335,14 +372,15 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
     const size_t ntiles = div_up(n, RS_TILE);
 
     if ((int)ntiles <= fused_tile_limit(dev)) {
-        Scratch hist(2 * ntiles * RS_BINS * sizeof(uint32_t), s);
+        const int fpasses = fused_passes(end_bit - begin_bit);
+        Scratch hist(2 * ntiles * RF_BINS * sizeof(uint32_t), s);
         uint32_t *tile_hist = hist.as<uint32_t>();
         uint32_t n32 = (uint32_t)n;
         void *args[] = {&a, &b, &n32, &begin_bit, &end_bit, &tile_hist};
-        launch("radix_fused_kernel", s, 16 * (size_t)n * npasses, [&] {
-            CWCU_CHECK(cudaLaunchCooperativeKernel((const void *)radix_fused_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, 0, s));
+        launch("radix_fused_kernel", s, 16 * (size_t)n * fpasses, [&] {
+            CWCU_CHECK(cudaLaunchCooperativeKernel((const void *)radix_fused_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, RF_SMEM_BYTES, s));
         });
-        return (npasses & 1) ? b : a;
+        return (fpasses & 1) ? b : a;
     }
 
     // [hist P*256 | binbase P*256 | tickets 8 | status P*ntiles*256] (u32 each)
