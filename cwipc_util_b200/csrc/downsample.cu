@@ -37,6 +37,13 @@ constexpr int WL_RADIX = 72;     // voxel-in-leaf coordinate range per axis (64 
 constexpr int WL_BITS = 19;      // 72^3 = 373248 < 2^19
 constexpr int MAX_OCTREE_DEPTH = 14;
 
+struct OctreeSeed { // box state to continue from (a cloud partitioned over several GPUs is replayed part by part)
+    double min[3];
+    double max[3];
+    int depth;
+    int valid; // 0: start from this cloud's first point
+};
+
 struct OctreeBox {
     double min[3];
     double max[3];
@@ -97,7 +104,7 @@ __device__ __forceinline__ bool violates(const double *mn, const double *mx, flo
 }
 
 __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__ pts, uint32_t n, const float *chunk_bbox, uint32_t nchunks, double res, int do_octree,
-                                                  OctreeBox *__restrict__ out) {
+                                                  const OctreeSeed &seed, OctreeBox *__restrict__ out) {
     __shared__ float s_red[6][32];
     __shared__ double s_min[3], s_max[3];
     __shared__ int s_depth, s_error;
@@ -138,7 +145,15 @@ __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__
     }
 
     const double eps = (double)1.1920929e-07f; // std::numeric_limits<float>::epsilon(), promoted as in PCL
-    if (tid == 0) {
+    if (tid == 0 && seed.valid) {
+        for (int a = 0; a < 3; a++) {
+            s_min[a] = seed.min[a];
+            s_max[a] = seed.max[a];
+        }
+        s_depth = seed.depth;
+        s_error = 0;
+        s_cursor = 0;
+    } else if (tid == 0) {
         const Point16 p0 = ld_point(pts, 0);
         const float c[3] = {p0.x, p0.y, p0.z};
         for (int a = 0; a < 3; a++) {
@@ -231,7 +246,7 @@ __device__ __forceinline__ void octree_box_block(const cwipc_point *__restrict__
 // One launch: every block boxes its 1024-point chunk; the block that finishes last reduces the chunk boxes
 // and replays the octree growth (the classic "last block" pattern: fence, ticket, fence).
 __global__ void __launch_bounds__(BB_THREADS) bbox_octree_kernel(const cwipc_point *__restrict__ pts, uint32_t n, float *chunk_bbox, uint32_t nchunks, double res, int do_octree,
-                                                                uint32_t *__restrict__ done_counter, OctreeBox *__restrict__ out) {
+                                                                OctreeSeed seed, uint32_t *__restrict__ done_counter, OctreeBox *__restrict__ out) {
     __shared__ bool s_last;
     chunk_bbox_block(pts, n, chunk_bbox);
     __threadfence();
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(BB_THREADS) bbox_octree_kernel(const cwipc_poi
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    octree_box_block(pts, n, chunk_bbox, nchunks, res, do_octree, out);
+    octree_box_block(pts, n, chunk_bbox, nchunks, res, do_octree, seed, out);
 }
 
 // ---- key generation --------------------------------------------------------------------------
@@ -497,22 +512,27 @@ struct Plan {
     int slotbits = 0;
 };
 
-// Runs the two bounding-box kernels, reads the box back (one sync) and derives the key layout.
-Plan make_plan(const cwipc_point *pts, size_t n, float cellsize, bool octree_split, int dev, cudaStream_t s) {
-    Plan plan;
+// One launch + one readback: bounding box of the points and the octree box after inserting them in order
+// (continuing from `seed` when it is valid).
+OctreeBox measure_box(const cwipc_point *pts, size_t n, float cellsize, bool octree_split, const OctreeSeed &seed, int dev, cudaStream_t s) {
     const uint32_t nchunks = (uint32_t)div_up(n, BB_CHUNK);
     Scratch chunk_bbox((size_t)nchunks * 6 * sizeof(float), s);
     Scratch box(sizeof(OctreeBox), s);
     const float octree_cellsize = 64 * cellsize;           // ref: src/cwipc_filters.cpp:113-114 (float)
     const double res = (double)octree_cellsize;
     launch("bbox_octree_kernel", s, 16 * (size_t)n, [&] {
-        bbox_octree_kernel<<<nchunks, BB_THREADS, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, bbox_counter(dev, s), box.as<OctreeBox>());
+        bbox_octree_kernel<<<nchunks, BB_THREADS, 0, s>>>(pts, (uint32_t)n, chunk_bbox.as<float>(), nchunks, res, octree_split ? 1 : 0, seed, bbox_counter(dev, s), box.as<OctreeBox>());
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
-    const OctreeBox ob = *h;
+    return *h;
+}
 
+// Key layout, hash-table size and limits from the measured (or supplied) boxes.
+Plan derive_plan(const OctreeBox &ob, size_t n, float cellsize, bool octree_split) {
+    Plan plan;
+    const double res = (double)(64 * cellsize);
     KeyParams &kp = plan.kp;
     memset(&kp, 0, sizeof(kp));
     kp.octree = octree_split ? 1 : 0;
@@ -577,7 +597,8 @@ unsigned stream_grid(size_t n, int dev) {
 
 } // namespace
 
-DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool octree_split, int dev, cudaStream_t s) {
+namespace {
+DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octree_split, const OctreeBox *external, int dev, cudaStream_t s) {
     DownsampleResult result;
     const size_t n = in->count;
     if (n == 0) {
@@ -596,7 +617,15 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
         result.error = "invalid voxel size " + std::to_string(cellsize);
         return result;
     }
-    Plan plan = make_plan(in->d_pts, n, cellsize, octree_split, dev, s);
+    OctreeBox ob;
+    if (external) {
+        ob = *external;
+    } else {
+        OctreeSeed none;
+        memset(&none, 0, sizeof(none));
+        ob = measure_box(in->d_pts, n, cellsize, octree_split, none, dev, s);
+    }
+    Plan plan = derive_plan(ob, n, cellsize, octree_split);
     if (plan.failed) {
         result.failed = true;
         result.error = plan.error;
@@ -657,12 +686,72 @@ DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool oc
     return result;
 }
 
+OctreeSeed no_seed() {
+    OctreeSeed none;
+    memset(&none, 0, sizeof(none));
+    return none;
+}
+} // namespace
+
+DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool octree_split, int dev, cudaStream_t s) {
+    return downsample_impl(in, cellsize, octree_split, nullptr, dev, s);
+}
+
+// Partitioned clouds: the octree box and the bounding box of the WHOLE cloud are supplied by the caller.
+DownsampleResult downsample_points_planned(const StoragePtr &in, float cellsize, bool octree_split, const OctreeState &state, const float bounds[6], int dev, cudaStream_t s) {
+    OctreeBox ob;
+    memset(&ob, 0, sizeof(ob));
+    for (int a = 0; a < 3; a++) {
+        ob.min[a] = state.min[a];
+        ob.max[a] = state.max[a];
+        ob.gmin[a] = bounds[a];
+        ob.gmax[a] = bounds[3 + a];
+    }
+    ob.depth = state.depth;
+    if (octree_split && !state.valid && in->count > 0) {
+        DownsampleResult r;
+        r.failed = true;
+        r.error = "planned downsample needs the octree state of the whole cloud";
+        return r;
+    }
+    return downsample_impl(in, cellsize, octree_split, &ob, dev, s);
+}
+
+// Continue the octree bounding-box replay over this cloud's points; also returns its bounding box.
+void octree_replay(const cwipc_point *in, size_t n, float cellsize, OctreeState &state, float bounds[6], int dev, cudaStream_t s) {
+    for (int a = 0; a < 3; a++) {
+        bounds[a] = INFINITY;
+        bounds[3 + a] = -INFINITY;
+    }
+    if (n == 0) return;
+    OctreeSeed seed;
+    memset(&seed, 0, sizeof(seed));
+    if (state.valid) {
+        for (int a = 0; a < 3; a++) {
+            seed.min[a] = state.min[a];
+            seed.max[a] = state.max[a];
+        }
+        seed.depth = state.depth;
+        seed.valid = 1;
+    }
+    const OctreeBox ob = measure_box(in, n, cellsize, true, seed, dev, s);
+    if (ob.error) throw CudaError{cudaErrorInvalidValue, "octree replay: runaway growth (non-finite coordinates?)"};
+    for (int a = 0; a < 3; a++) {
+        state.min[a] = ob.min[a];
+        state.max[a] = ob.max[a];
+        bounds[a] = ob.gmin[a];
+        bounds[3 + a] = ob.gmax[a];
+    }
+    state.depth = ob.depth;
+    state.valid = 1;
+}
+
 void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], int dev, cudaStream_t s) {
     const uint32_t nchunks = (uint32_t)div_up(n, BB_CHUNK);
     Scratch chunk_bbox((size_t)nchunks * 6 * sizeof(float), s);
     Scratch box(sizeof(OctreeBox), s);
     launch("bbox_octree_kernel", s, 16 * (size_t)n, [&] {
-        bbox_octree_kernel<<<nchunks, BB_THREADS, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, bbox_counter(dev, s), box.as<OctreeBox>());
+        bbox_octree_kernel<<<nchunks, BB_THREADS, 0, s>>>(in, (uint32_t)n, chunk_bbox.as<float>(), nchunks, 1.0, 0, no_seed(), bbox_counter(dev, s), box.as<OctreeBox>());
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
@@ -676,7 +765,7 @@ void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], 
 void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_split, uint64_t *host_keys, int dev, cudaStream_t s) {
     const size_t n = in->count;
     if (n == 0) return;
-    Plan plan = make_plan(in->d_pts, n, cellsize, octree_split, dev, s);
+    Plan plan = derive_plan(measure_box(in->d_pts, n, cellsize, octree_split, no_seed(), dev, s), n, cellsize, octree_split);
     if (plan.failed) throw CudaError{cudaErrorInvalidValue, plan.error};
     Scratch keys(n * sizeof(uint64_t), s);
     Scratch flag(sizeof(uint32_t), s);

@@ -243,6 +243,173 @@ int cwipc_cuda_knn_mean_distances(cwipc_pointcloud *pc, int kNeighbors, float *d
     });
 }
 
+// ---- partitioned clouds: building blocks for a cloud spread over several GPUs as x-slabs ---------------
+// The collective steps (who sends what to whom) are the caller's; see cwipc_util_b200/slab.py.
+
+int cwipc_cuda_octree_replay(cwipc_pointcloud *pc, float cellsize, struct cwipc_cuda_octree_state *state, float bounds[6]) {
+    if (pc == nullptr || state == nullptr || bounds == nullptr) return -1;
+    return guarded<int>("cwipc_cuda_octree_replay", -1, [&]() -> int {
+        StoragePtr in = storage_of(pc, "cwipc_cuda_octree_replay");
+        if (!in || !(cellsize > 0.f)) return -1;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        OctreeState st;
+        memcpy(st.min, state->min, sizeof(st.min));
+        memcpy(st.max, state->max, sizeof(st.max));
+        st.depth = state->depth;
+        st.valid = state->valid;
+        octree_replay(in->d_pts, in->count, cellsize, st, bounds, in->dev, s);
+        in->release_after_read(s);
+        memcpy(state->min, st.min, sizeof(st.min));
+        memcpy(state->max, st.max, sizeof(st.max));
+        state->depth = st.depth;
+        state->valid = st.valid;
+        return 0;
+    });
+}
+
+cwipc_pointcloud *cwipc_cuda_downsample_planned(cwipc_pointcloud *pc, float voxelsize, const struct cwipc_cuda_octree_state *state, const float bounds[6]) {
+    if (pc == nullptr || state == nullptr || bounds == nullptr) return nullptr;
+    const bool octree_split = !(voxelsize < 0);
+    float cellsize = octree_split ? voxelsize : -voxelsize;
+    return guarded<cwipc_pointcloud *>("cwipc_cuda_downsample_planned", nullptr, [&]() -> cwipc_pointcloud * {
+        if (pc->cellsize() >= cellsize) cellsize = pc->cellsize();
+        StoragePtr in = storage_of(pc, "cwipc_cuda_downsample_planned");
+        if (!in) return nullptr;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        OctreeState st;
+        memcpy(st.min, state->min, sizeof(st.min));
+        memcpy(st.max, state->max, sizeof(st.max));
+        st.depth = state->depth;
+        st.valid = state->valid;
+        DownsampleResult r;
+        try {
+            if (in->count == 0) {
+                r.out = std::make_shared<Storage>(in->dev, 0, s); // an empty part contributes nothing
+                r.out->mark_ready();
+            } else {
+                r = downsample_points_planned(in, cellsize, octree_split, st, bounds, in->dev, s);
+            }
+        } catch (...) {
+            in->release_after_read(s);
+            throw;
+        }
+        in->release_after_read(s);
+        if (r.failed || !r.out) {
+            log(CWIPC_LOG_LEVEL_ERROR, "cwipc_cuda_downsample_planned", r.error.empty() ? std::string("downsample failed") : r.error);
+            return nullptr;
+        }
+        auto *rv = new DevicePointcloud(r.out, pc->timestamp(), 0.f);
+        rv->_set_cellsize(cellsize);
+        return rv;
+    });
+}
+
+cwipc_pointcloud *cwipc_cuda_from_device_points(const void *dev_points, int npoint, uint64_t timestamp) {
+    if (npoint < 0 || (npoint > 0 && dev_points == nullptr)) return nullptr;
+    return guarded<cwipc_pointcloud *>("cwipc_cuda_from_device_points", nullptr, [&]() -> cwipc_pointcloud * {
+        const int dev = current_device();
+        DeviceGuard g(dev);
+        cudaStream_t s = thread_stream(dev);
+        auto out = std::make_shared<Storage>(dev, (size_t)npoint, s);
+        out->count = (size_t)npoint;
+        if (npoint) CWCU_CHECK(cudaMemcpyAsync(out->d_pts, dev_points, (size_t)npoint * sizeof(cwipc_point), cudaMemcpyDefault, s));
+        out->mark_ready();
+        CWCU_CHECK(cudaStreamSynchronize(s)); // the caller may reuse its buffer on return
+        return new DevicePointcloud(out, timestamp, 0.f);
+    });
+}
+
+int cwipc_cuda_knn_query(cwipc_pointcloud *pc, int kNeighbors, int nquery, float *mean, float *kth2) {
+    if (pc == nullptr || mean == nullptr || nquery < 0) return -1;
+    return guarded<int>("cwipc_cuda_knn_query", -1, [&]() -> int {
+        StoragePtr in = storage_of(pc, "cwipc_cuda_knn_query");
+        if (!in || (size_t)nquery > in->count) return -1;
+        if (nquery == 0) return 0;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        Scratch d(in->count * sizeof(float), s), kth(in->count * sizeof(float), s);
+        float box[6];
+        knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), bounds_of(*in, box), d.as<float>(), in->dev, s, kth.as<float>(), (size_t)nquery);
+        CWCU_CHECK(cudaMemcpyAsync(mean, d.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (kth2) CWCU_CHECK(cudaMemcpyAsync(kth2, kth.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToHost, s));
+        in->release_after_read(s);
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        return nquery;
+    });
+}
+
+int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, int nq, int kNeighbors, float *lists) {
+    if (pc == nullptr || nq < 0 || (nq > 0 && (queries == nullptr || lists == nullptr))) return -1;
+    return guarded<int>("cwipc_cuda_knn_lists", -1, [&]() -> int {
+        StoragePtr in = storage_of(pc, "cwipc_cuda_knn_lists");
+        if (!in) return -1;
+        if (nq == 0) return 0;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        in->acquire_for_read(s);
+        const size_t kk = (size_t)kNeighbors + 1;
+        Scratch q((size_t)nq * sizeof(cwipc_point), s), l((size_t)nq * kk * sizeof(float), s);
+        CWCU_CHECK(cudaMemcpyAsync(q.p, queries, (size_t)nq * sizeof(cwipc_point), cudaMemcpyHostToDevice, s));
+        float box[6];
+        knn_lists(in->d_pts, in->count, q.as<cwipc_point>(), (size_t)nq, kNeighbors, pc->cellsize(), bounds_of(*in, box), l.as<float>(), in->dev, s);
+        CWCU_CHECK(cudaMemcpyAsync(lists, l.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, s));
+        in->release_after_read(s);
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        return nq;
+    });
+}
+
+int cwipc_cuda_knn_merge_lists(const float *lists, int nlists, int nq, int kNeighbors, float *mean, float *kth2) {
+    if (nq < 0 || nlists < 1 || (nq > 0 && (lists == nullptr || mean == nullptr))) return -1;
+    return guarded<int>("cwipc_cuda_knn_merge_lists", -1, [&]() -> int {
+        if (nq == 0) return 0;
+        const int dev = current_device();
+        DeviceGuard g(dev);
+        cudaStream_t s = thread_stream(dev);
+        const size_t kk = (size_t)kNeighbors + 1, total = (size_t)nlists * nq * kk;
+        Scratch l(total * sizeof(float), s), m((size_t)nq * sizeof(float), s), kt((size_t)nq * sizeof(float), s);
+        CWCU_CHECK(cudaMemcpyAsync(l.p, lists, total * sizeof(float), cudaMemcpyHostToDevice, s));
+        knn_merge_lists(l.as<float>(), (size_t)nlists, (size_t)nq, kNeighbors, m.as<float>(), kt.as<float>(), s);
+        CWCU_CHECK(cudaMemcpyAsync(mean, m.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (kth2) CWCU_CHECK(cudaMemcpyAsync(kth2, kt.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        return nq;
+    });
+}
+
+int cwipc_cuda_distance_stats(const float *dist, size_t ndist, double sums[2]) {
+    if (sums == nullptr || (ndist > 0 && dist == nullptr)) return -1;
+    return guarded<int>("cwipc_cuda_distance_stats", -1, [&]() -> int {
+        const int dev = current_device();
+        DeviceGuard g(dev);
+        cudaStream_t s = thread_stream(dev);
+        Scratch d(ndist * sizeof(float), s);
+        if (ndist) CWCU_CHECK(cudaMemcpyAsync(d.p, dist, ndist * sizeof(float), cudaMemcpyHostToDevice, s));
+        distance_stats(d.as<float>(), ndist, sums, s);
+        return 0;
+    });
+}
+
+double cwipc_cuda_outlier_threshold(double sum, double sq, double n, float stddevMulThresh) { return outlier_threshold(sum, sq, n, stddevMulThresh); }
+
+cwipc_pointcloud *cwipc_cuda_filter_by_distance(cwipc_pointcloud *pc, const float *dist, size_t ndist, double threshold) {
+    return unary_filter("cwipc_cuda_filter_by_distance", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        if (ndist != in->count || (ndist > 0 && dist == nullptr)) throw CudaError{cudaErrorInvalidValue, "one distance per point is required"};
+        Scratch d(ndist * sizeof(float), s);
+        if (ndist) CWCU_CHECK(cudaMemcpyAsync(d.p, dist, ndist * sizeof(float), cudaMemcpyHostToDevice, s));
+        Predicate p;
+        p.kind = PredKind::DistanceAtMost;
+        p.dist = d.as<float>();
+        p.threshold = threshold;
+        return compact_to_new(in, p, dev, s);
+    });
+}
+
 int cwipc_cuda_downsample_keys(cwipc_pointcloud *pc, float voxelsize, uint64_t *keys, size_t nkeys) {
     if (pc == nullptr || keys == nullptr) return -1;
     return guarded<int>("cwipc_cuda_downsample_keys", -1, [&]() -> int {

@@ -36,6 +36,15 @@ struct DownsampleResult {
 // cellsize > 0 already resolved against the cloud's own cellsize.  octree_split selects the
 // reference's positive-size path (per-octree-leaf grids) vs the single global grid.
 DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool octree_split, int dev, cudaStream_t s);
+// Octree bounding box of pcl::octree::OctreePointCloud after inserting points in order (a cloud partitioned
+// over several GPUs is replayed part by part, the state travelling from rank to rank).
+struct OctreeState {
+    double min[3] = {0, 0, 0}, max[3] = {0, 0, 0};
+    int depth = 0;
+    int valid = 0;
+};
+void octree_replay(const cwipc_point *in, size_t n, float cellsize, OctreeState &state, float bounds[6], int dev, cudaStream_t s);
+DownsampleResult downsample_points_planned(const StoragePtr &in, float cellsize, bool octree_split, const OctreeState &state, const float bounds[6], int dev, cudaStream_t s);
 // global bounding box of in[0..n), n > 0 (synchronises the stream)
 void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], int dev, cudaStream_t s);
 // diagnostic: sort keys (without the index bits) per input point, to host
@@ -47,7 +56,17 @@ void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_s
 // `bounds` (min xyz, max xyz), when not null, is a box known to contain every point; it saves the bounding-box pass.
 size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, const float *bounds, int dev, cudaStream_t s);
 // First pass only: mean distance to the k nearest neighbours per point, original order, device array.
-void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s);
+// Only the first `nquery` points are queries (the rest are candidates only); d_kth, when not null, receives the
+// (k+1)-th smallest squared distance of every query.
+void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s, float *d_kth = nullptr,
+                        size_t nquery = (size_t)-1);
+// The k+1 smallest squared distances (ascending, +inf padded) from each of nq device-resident query points to the cloud.
+void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev, cudaStream_t s);
+// lists laid out [nlists][nq][k+1]; mean distance to the k nearest (and k-th squared distance) of the merged lists
+void knn_merge_lists(const float *d_lists, size_t nlists, size_t nq, int k, float *d_mean, float *d_kth, cudaStream_t s);
+// sum d, sum (float)(d*d), both in double (synchronises the stream)
+void distance_stats(const float *d_dist, size_t n, double out[2], cudaStream_t s);
+double outlier_threshold(double sum, double sq, double n, float stddev_mul);
 
 // ---- runtime.cu ----------------------------------------------------------------------------
 void flush_l2(int dev, cudaStream_t s);

@@ -240,8 +240,8 @@ __device__ __forceinline__ float warp_max(float v) {
 
 template <int KCAP>
 __global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
-                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, FarEntry *__restrict__ far_list,
-                                                               uint32_t *__restrict__ far_count) {
+                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out, uint32_t nquery,
+                                                               FarEntry *__restrict__ far_list, uint32_t *__restrict__ far_count) {
     extern __shared__ __align__(128) unsigned char knn_smem_raw[];
     constexpr int B = KCAP < KT_BUF ? KCAP : KT_BUF;
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -267,9 +267,10 @@ __global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point 
 
     for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += warps_total) {
         const uint32_t qi = item * 32u + lane;
-        const bool active = qi < n;
-        const uint32_t qs = active ? qi : n - 1u;
+        const uint32_t qs = qi < n ? qi : n - 1u;
         const uint64_t word = sorted[qs];
+        // only the first `nquery` points (original order) are queries; the rest are candidates only (halo points)
+        const bool active = qi < n && (uint32_t)(word & idxmask) < nquery;
         const uint64_t code = word >> gp.idxbits;
         const Point16 q = spts16[qs];
         const float ux = cell_u(q.x, gp.gmin[0], gp.inv_h), uy = cell_u(q.y, gp.gmin[1], gp.inv_h), uz = cell_u(q.z, gp.gmin[2], gp.inv_h);
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point 
                 for (int j = 0; j < KCAP; j++)
                     if (j > extra) sum += sqrt((double)best[j]); // j == extra is the query itself (distance 0)
                 dist_out[(size_t)(word & idxmask)] = (float)(sum / (double)k);
+                if (kth_out) kth_out[(size_t)(word & idxmask)] = worst;
             } else {
                 const uint32_t slot = atomicAdd(far_count, 1u);
                 FarEntry e;
@@ -443,111 +445,116 @@ __device__ __forceinline__ float warp_bitonic_merge32(float x, unsigned lane) { 
     return x;
 }
 
+// The kk nearest squared distances from q to the cloud, ascending along (lane, register): element e
+// lives in lane e % 32, register e / 32.  Called by all 32 lanes of a warp with the same arguments.
+template <int KPL>
+__device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Point16 *__restrict__ spts16, uint32_t n, const GridParams &gp, int kk,
+                                        const uint2 *__restrict__ table, uint32_t leaf_points, FarNode *stack, float (&v)[KPL]) {
+    const unsigned lane = lane_id();
+    const float slack = 0.01f * gp.h;
+#pragma unroll
+    for (int j = 0; j < KPL; j++) v[j] = INFINITY;
+    float tau = INFINITY; // current kk-th smallest
+
+    if (lane == 0) {
+        FarNode root;
+        root.pb = 0; root.pe = n; root.x = root.y = root.z = 0; root.level = gp.top_level; root.mind2 = 0.f; root.pad = 0;
+        stack[0] = root;
+    }
+    int sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        const FarNode node = stack[--sp];
+        __syncwarp();
+        const float thr = fminf(tau, limit);
+        if (node.mind2 * 0.9999f > thr) continue;
+        if (node.level == 0 || node.pe - node.pb <= leaf_points) {
+            for (uint32_t base = node.pb; base < node.pe; base += 32) {
+                const uint32_t c = base + lane;
+                float d2 = INFINITY;
+                if (c < node.pe) d2 = dist2(q, spts16[c]);
+                const bool pass = d2 < tau && d2 <= limit;
+                unsigned pm = __ballot_sync(FULL_MASK, pass);
+                if (pm == 0u) continue;
+                if (KPL == 1 && __popc(pm) <= 6) {
+                    // few survivors: insert them one by one into the lane-distributed sorted list
+                    while (pm) {
+                        const int src = __ffs(pm) - 1;
+                        pm &= pm - 1;
+                        const float x = __shfl_sync(FULL_MASK, d2, src);
+                        const float up = __shfl_up_sync(FULL_MASK, v[0], 1);
+                        if (v[0] > x) v[0] = (lane == 0) ? x : fmaxf(up, x);
+                    }
+                    tau = __shfl_sync(FULL_MASK, v[0], (kk - 1) & 31);
+                    continue;
+                }
+                const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
+                const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
+                if (KPL == 1) {
+                    v[0] = warp_bitonic_merge32(fminf(v[0], r), lane);
+                } else {
+                    v[KPL - 1] = fminf(v[KPL - 1], r);
+                    const float lo = fminf(v[0], v[KPL - 1]), hi = fmaxf(v[0], v[KPL - 1]);
+                    v[0] = warp_bitonic_merge32(lo, lane);
+                    v[KPL - 1] = warp_bitonic_merge32(hi, lane);
+                }
+                tau = __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
+            }
+        } else {
+            // children at level-1: lanes 0..7 look one child up each
+            const int cl = node.level - 1;
+            const uint32_t chx = 2u * node.x + ((lane >> 2) & 1u), chy = 2u * node.y + ((lane >> 1) & 1u), chz = 2u * node.z + (lane & 1u);
+            uint2 r = make_uint2(0u, 0u);
+            float mind2 = INFINITY;
+            bool admit = false;
+            if (lane < 8 && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl)) {
+                r = table[table_index(gp, cl, chx, chy, chz)];
+                if (r.y > r.x) {
+                    const float pitch = ldexpf(gp.h, cl);
+                    const float lo[3] = {gp.gmin[0] + (float)chx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
+                    const float qq[3] = {q.x, q.y, q.z};
+                    mind2 = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
+                        mind2 += d * d;
+                    }
+                    admit = mind2 * 0.9999f <= thr;
+                }
+            }
+            const unsigned adm = __ballot_sync(FULL_MASK, admit);
+            const int nadm = __popc(adm);
+            int rank = 0; // position among the admitted children, nearest first
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float mj = __shfl_sync(FULL_MASK, mind2, j);
+                if (((adm >> j) & 1u) && (mj < mind2 || (mj == mind2 && j < (int)lane))) rank++;
+            }
+            if (admit) {
+                FarNode ch;
+                ch.pb = r.x; ch.pe = r.y; ch.x = chx; ch.y = chy; ch.z = chz; ch.level = cl; ch.mind2 = mind2; ch.pad = 0;
+                stack[sp + nadm - 1 - rank] = ch; // farthest deepest, nearest on top
+            }
+            sp += nadm;
+            __syncwarp();
+        }
+    }
+}
+
 template <int KPL>
 __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
-                                                              const uint2 *__restrict__ table, float *__restrict__ dist_out, const FarEntry *__restrict__ far_list,
-                                                              const uint32_t *__restrict__ far_count, uint32_t leaf_points) {
+                                                              const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out,
+                                                              const FarEntry *__restrict__ far_list, const uint32_t *__restrict__ far_count, uint32_t leaf_points) {
     __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    FarNode *stack = s_stack[warp];
     const uint32_t nentries = *far_count;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint64_t idxmask = (1ull << gp.idxbits) - 1ull;
     const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
-    const float slack = 0.01f * gp.h;
-
     for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < nentries; ei += warps_total) {
         const FarEntry ent = far_list[ei];
-        const Point16 q = spts16[ent.q];
-        const float limit = ent.bound; // at least kk points lie within `limit` when it is finite
         float v[KPL];
-#pragma unroll
-        for (int j = 0; j < KPL; j++) v[j] = INFINITY;
-        float tau = INFINITY; // current kk-th smallest
-
-        if (lane == 0) {
-            FarNode root;
-            root.pb = 0; root.pe = n; root.x = root.y = root.z = 0; root.level = gp.top_level; root.mind2 = 0.f; root.pad = 0;
-            stack[0] = root;
-        }
-        int sp = 1;
-        __syncwarp();
-        while (sp > 0) {
-            const FarNode node = stack[--sp];
-            __syncwarp();
-            const float thr = fminf(tau, limit);
-            if (node.mind2 * 0.9999f > thr) continue;
-            if (node.level == 0 || node.pe - node.pb <= leaf_points) {
-                for (uint32_t base = node.pb; base < node.pe; base += 32) {
-                    const uint32_t c = base + lane;
-                    float d2 = INFINITY;
-                    if (c < node.pe) d2 = dist2(q, spts16[c]);
-                    const bool pass = d2 < tau && d2 <= limit;
-                    unsigned pm = __ballot_sync(FULL_MASK, pass);
-                    if (pm == 0u) continue;
-                    if (KPL == 1 && __popc(pm) <= 6) {
-                        // few survivors: insert them one by one into the lane-distributed sorted list
-                        while (pm) {
-                            const int src = __ffs(pm) - 1;
-                            pm &= pm - 1;
-                            const float x = __shfl_sync(FULL_MASK, d2, src);
-                            const float up = __shfl_up_sync(FULL_MASK, v[0], 1);
-                            if (v[0] > x) v[0] = (lane == 0) ? x : fmaxf(up, x);
-                        }
-                        tau = __shfl_sync(FULL_MASK, v[0], (kk - 1) & 31);
-                        continue;
-                    }
-                    const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
-                    const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
-                    if (KPL == 1) {
-                        v[0] = warp_bitonic_merge32(fminf(v[0], r), lane);
-                    } else {
-                        v[KPL - 1] = fminf(v[KPL - 1], r);
-                        const float lo = fminf(v[0], v[KPL - 1]), hi = fmaxf(v[0], v[KPL - 1]);
-                        v[0] = warp_bitonic_merge32(lo, lane);
-                        v[KPL - 1] = warp_bitonic_merge32(hi, lane);
-                    }
-                    tau = __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
-                }
-            } else {
-                // children at level-1: lanes 0..7 look one child up each
-                const int cl = node.level - 1;
-                const uint32_t chx = 2u * node.x + ((lane >> 2) & 1u), chy = 2u * node.y + ((lane >> 1) & 1u), chz = 2u * node.z + (lane & 1u);
-                uint2 r = make_uint2(0u, 0u);
-                float mind2 = INFINITY;
-                bool admit = false;
-                if (lane < 8 && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl)) {
-                    r = table[table_index(gp, cl, chx, chy, chz)];
-                    if (r.y > r.x) {
-                        const float pitch = ldexpf(gp.h, cl);
-                        const float lo[3] = {gp.gmin[0] + (float)chx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
-                        const float qq[3] = {q.x, q.y, q.z};
-                        mind2 = 0.f;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
-                            mind2 += d * d;
-                        }
-                        admit = mind2 * 0.9999f <= thr;
-                    }
-                }
-                const unsigned adm = __ballot_sync(FULL_MASK, admit);
-                const int nadm = __popc(adm);
-                int rank = 0; // position among the admitted children, nearest first
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float mj = __shfl_sync(FULL_MASK, mind2, j);
-                    if (((adm >> j) & 1u) && (mj < mind2 || (mj == mind2 && j < (int)lane))) rank++;
-                }
-                if (admit) {
-                    FarNode ch;
-                    ch.pb = r.x; ch.pe = r.y; ch.x = chx; ch.y = chy; ch.z = chz; ch.level = cl; ch.mind2 = mind2; ch.pad = 0;
-                    stack[sp + nadm - 1 - rank] = ch; // farthest deepest, nearest on top
-                }
-                sp += nadm;
-                __syncwarp();
-            }
-        }
+        dfs_knn<KPL>(spts16[ent.q], ent.bound, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v);
         // sum of sqrt over elements 1..k in ascending order (double), as the reference does
         double sq[KPL];
 #pragma unroll
@@ -557,8 +564,63 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
             const double t = __shfl_sync(FULL_MASK, e < 32 ? sq[0] : sq[KPL - 1], e & 31);
             sum += t;
         }
-        if (lane == 0) dist_out[(size_t)(sorted[ent.q] & idxmask)] = (float)(sum / (double)k);
+        const float kth = __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
+        if (lane == 0) {
+            const size_t orig = (size_t)(sorted[ent.q] & idxmask);
+            dist_out[orig] = (float)(sum / (double)k);
+            if (kth_out) kth_out[orig] = kth;
+        }
     }
+}
+
+// External queries (any position, not members of the cloud): the kk smallest squared distances each, ascending.
+// Used when a cloud is partitioned over several GPUs: every part answers, the owner merges the lists.
+template <int KPL>
+__global__ void __launch_bounds__(KF_THREADS) knn_list_kernel(const cwipc_point *__restrict__ spts, uint32_t n, GridParams gp, int kk, const uint2 *__restrict__ table,
+                                                               const cwipc_point *__restrict__ queries, uint32_t nq, float *__restrict__ lists, uint32_t leaf_points) {
+    __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
+    for (uint32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < nq; qi += warps_total) {
+        float v[KPL];
+        dfs_knn<KPL>(ld_point(queries, qi), INFINITY, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v);
+#pragma unroll
+        for (int j = 0; j < KPL; j++) {
+            const int e = j * 32 + (int)lane;
+            if (e < kk) lists[(size_t)qi * kk + e] = v[j]; // +inf pads when the cloud holds fewer than kk points
+        }
+    }
+}
+
+// Merge `nlists` ascending lists of kk squared distances per query into the mean distance to the k nearest
+// (element 0 of the merged list is the query itself).  One thread per query; the lists are tiny.
+__global__ void __launch_bounds__(128) knn_merge_lists_kernel(const float *__restrict__ lists, uint32_t nlists, uint32_t nq, int kk, int k, float *__restrict__ mean,
+                                                               float *__restrict__ kth_out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t head[16]; // next unread element of each list (nlists <= 16)
+    for (uint32_t l = 0; l < nlists; l++) head[l] = 0;
+    double sum = 0.0;
+    float last = 0.f;
+    for (int e = 0; e < kk; e++) {
+        float best = INFINITY;
+        uint32_t arg = 0;
+        for (uint32_t l = 0; l < nlists; l++) {
+            if (head[l] < (uint32_t)kk) {
+                const float x = lists[((size_t)l * nq + q) * kk + head[l]];
+                if (x < best) {
+                    best = x;
+                    arg = l;
+                }
+            }
+        }
+        head[arg]++;
+        if (e > 0) sum += sqrt((double)best);
+        last = best;
+    }
+    mean[q] = (float)(sum / (double)k);
+    if (kth_out) kth_out[q] = last;
 }
 
 // ---- statistics: fixed-order two-level double reduction -------------------------------------------
@@ -663,9 +725,15 @@ GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, 
     return plan;
 }
 
+uint32_t far_leaf_points() {
+    // nodes with at most this many points are scanned directly instead of being expanded
+    static const uint32_t v = (uint32_t)env_float("CWIPC_CUDA_KNN_LEAF", 128.f, 1.f, 65536.f);
+    return v;
+}
+
 template <int KCAP>
-void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const GridParams &gp, int k, const uint2 *table, float *d_dist, FarEntry *far_list,
-             uint32_t *far_count, int dev, cudaStream_t s) {
+void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const GridParams &gp, int k, const uint2 *table, float *d_dist, float *d_kth, size_t nquery,
+             FarEntry *far_list, uint32_t *far_count, int dev, cudaStream_t s) {
     const int kk = k + 1;
     const size_t smem = sizeof(KnnWarpSmem) * KT_WARPS;
     static std::once_flag once[64];
@@ -673,24 +741,24 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     const size_t nitems = div_up(n, (size_t)32);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nitems, (size_t)KT_WARPS), (size_t)sm_count(dev) * 2));
     launch("knn_tile_kernel", s, 28 * (size_t)n, [&] {
-        knn_tile_kernel<KCAP><<<grid, KT_THREADS, smem, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, far_list, far_count);
+        knn_tile_kernel<KCAP><<<grid, KT_THREADS, smem, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, (uint32_t)nquery, far_list, far_count);
     });
     if (gp.top_level == 0) return; // one cell spans the cloud: the main pass is exact for every query
     constexpr int KPL = KCAP > 32 ? 2 : 1;
-    // nodes with at most this many points are scanned directly instead of being expanded
-    static const uint32_t leaf_points = (uint32_t)env_float("CWIPC_CUDA_KNN_LEAF", 128.f, 1.f, 65536.f);
     launch("knn_far_kernel", s, (size_t)0, [&] {
-        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 4, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, far_list, far_count, leaf_points);
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 4, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, far_leaf_points());
     });
 }
 
-} // namespace
+// The search structure of one cloud: cell-ordered points + table pyramid (scratch lives as long as the object).
+struct KnnIndex {
+    GridParams gp;
+    Scratch keys_a, keys_b, spts, table;
+    const uint64_t *sorted = nullptr;
+    uint32_t *far_count = nullptr;
+};
 
-void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s) {
-    if (n == 0) return;
-    if (k < 1) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors must be >= 1"};
-    if (k + 1 > 64) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > 63 is not supported by libcwipc_util_cuda"};
-    if ((size_t)k >= n) throw CudaError{cudaErrorInvalidValue, "remove_outliers: needs more than kNeighbors points"};
+void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, int dev, cudaStream_t s) {
     float gmin[3], gmax[3];
     if (bounds) {
         for (int a = 0; a < 3; a++) {
@@ -703,34 +771,103 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     for (int a = 0; a < 3; a++)
         if (!std::isfinite(gmin[a]) || !std::isfinite(gmax[a])) throw CudaError{cudaErrorInvalidValue, "remove_outliers: pointcloud contains non-finite coordinates"};
     const GridPlan plan = choose_grid(gmin, gmax, n, k, hint_spacing);
-    const GridParams &gp = plan.gp;
+    ix.gp = plan.gp;
+    const GridParams &gp = ix.gp;
     int axis_bits = 1;
     for (int a = 0; a < 3; a++) axis_bits = std::max(axis_bits, bit_length((uint64_t)gp.gdim[a] - 1));
     const int keybits = 3 * axis_bits;
 
-    Scratch keys_a(n * sizeof(uint64_t), s), keys_b(n * sizeof(uint64_t), s);
-    launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] { knn_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in, (uint32_t)n, gp, keys_a.as<uint64_t>()); });
-    const uint64_t *sorted = radix_sort_u64(keys_a.as<uint64_t>(), keys_b.as<uint64_t>(), n, gp.idxbits, gp.idxbits + keybits, dev, s);
+    ix.keys_a = Scratch(n * sizeof(uint64_t), s);
+    ix.keys_b = Scratch(n * sizeof(uint64_t), s);
+    launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] { knn_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in, (uint32_t)n, gp, ix.keys_a.as<uint64_t>()); });
+    ix.sorted = radix_sort_u64(ix.keys_a.as<uint64_t>(), ix.keys_b.as<uint64_t>(), n, gp.idxbits, gp.idxbits + keybits, dev, s);
 
     // cell-ordered points, table pyramid, far-query counter
-    Scratch spts(n * sizeof(cwipc_point), s);
-    Scratch table(plan.table_entries * sizeof(uint2) + 16, s);
-    CWCU_CHECK(cudaMemsetAsync(table.p, 0, plan.table_entries * sizeof(uint2) + 16, s));
-    uint32_t *far_count = reinterpret_cast<uint32_t *>(table.as<uint2>() + plan.table_entries);
+    ix.spts = Scratch(n * sizeof(cwipc_point), s);
+    ix.table = Scratch(plan.table_entries * sizeof(uint2) + 16, s);
+    CWCU_CHECK(cudaMemsetAsync(ix.table.p, 0, plan.table_entries * sizeof(uint2) + 16, s));
+    ix.far_count = reinterpret_cast<uint32_t *>(ix.table.as<uint2>() + plan.table_entries);
     launch("knn_layout_kernel", s, 48 * (size_t)n, [&] {
-        knn_layout_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp, in, spts.as<cwipc_point>(), table.as<uint2>());
+        knn_layout_kernel<<<stream_grid(n, dev), 256, 0, s>>>(ix.sorted, (uint32_t)n, gp, in, ix.spts.as<cwipc_point>(), ix.table.as<uint2>());
     });
+}
 
+void check_k(int k, size_t n) {
+    if (k < 1) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors must be >= 1"};
+    if (k + 1 > 64) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > 63 is not supported by libcwipc_util_cuda"};
+    (void)n;
+}
+
+} // namespace
+
+void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s, float *d_kth, size_t nquery) {
+    if (n == 0) return;
+    check_k(k, n);
+    if ((size_t)k >= n) throw CudaError{cudaErrorInvalidValue, "remove_outliers: needs more than kNeighbors points"};
+    KnnIndex ix;
+    build_index(ix, in, n, k, hint_spacing, bounds, dev, s);
     // a query is queued at most once
     Scratch far_list((n + 64) * sizeof(FarEntry), s);
     const int kk = k + 1;
     auto go = [&](auto kcap) {
-        run_knn<decltype(kcap)::value>(spts.as<cwipc_point>(), sorted, n, gp, k, table.as<uint2>(), d_dist, far_list.as<FarEntry>(), far_count, dev, s);
+        run_knn<decltype(kcap)::value>(ix.spts.as<cwipc_point>(), ix.sorted, n, ix.gp, k, ix.table.as<uint2>(), d_dist, d_kth, std::min(nquery, n), far_list.as<FarEntry>(),
+                                       ix.far_count, dev, s);
     };
     if (kk <= 8) go(std::integral_constant<int, 8>{});
     else if (kk <= 16) go(std::integral_constant<int, 16>{});
     else if (kk <= 32) go(std::integral_constant<int, 32>{});
     else go(std::integral_constant<int, 64>{});
+}
+
+void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev, cudaStream_t s) {
+    check_k(k, n);
+    if (nq == 0) return;
+    const int kk = k + 1;
+    if (n == 0) { // nothing to answer with: every list is all +inf (0x7f800000)
+        std::vector<float> inf(nq * (size_t)kk, INFINITY);
+        CWCU_CHECK(cudaMemcpyAsync(d_lists, inf.data(), inf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        return;
+    }
+    KnnIndex ix;
+    build_index(ix, in, n, k, hint_spacing, bounds, dev, s);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nq, (size_t)KF_WARPS), (size_t)sm_count(dev) * 4));
+    launch("knn_list_kernel", s, (size_t)0, [&] {
+        if (kk <= 32)
+            knn_list_kernel<1><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, (uint32_t)nq, d_lists, far_leaf_points());
+        else
+            knn_list_kernel<2><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, (uint32_t)nq, d_lists, far_leaf_points());
+    });
+}
+
+void knn_merge_lists(const float *d_lists, size_t nlists, size_t nq, int k, float *d_mean, float *d_kth, cudaStream_t s) {
+    if (nq == 0) return;
+    if (nlists == 0 || nlists > 16) throw CudaError{cudaErrorInvalidValue, "knn_merge_lists: between 1 and 16 lists per query"};
+    launch("knn_merge_lists_kernel", s, (size_t)0, [&] {
+        knn_merge_lists_kernel<<<(unsigned)div_up(nq, 128), 128, 0, s>>>(d_lists, (uint32_t)nlists, (uint32_t)nq, k + 1, k, d_mean, d_kth);
+    });
+}
+
+void distance_stats(const float *d_dist, size_t n, double out[2], cudaStream_t s) {
+    out[0] = out[1] = 0.0;
+    if (n == 0) return;
+    Scratch partial(2 * ST_BLOCKS * sizeof(double), s);
+    launch("stats_kernel", s, 4 * n, [&] { stats_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(d_dist, (uint32_t)n, partial.as<double>()); });
+    double *h = static_cast<double *>(thread_pinned(2 * ST_BLOCKS * sizeof(double)));
+    CWCU_CHECK(cudaMemcpyAsync(h, partial.p, 2 * ST_BLOCKS * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CWCU_CHECK(cudaStreamSynchronize(s));
+    for (int b = 0; b < ST_BLOCKS; b++) {
+        out[0] += h[2 * b];
+        out[1] += h[2 * b + 1];
+    }
+}
+
+// ref: pcl statistical_outlier_removal.hpp -- mean, unbiased variance, threshold in double
+double outlier_threshold(double sum, double sq, double n, float stddev_mul) {
+    const double mean = sum / n;
+    const double variance = (sq - sum * sum / n) / (n - 1.0);
+    const double stddev = std::sqrt(variance);
+    return mean + (double)stddev_mul * stddev;
 }
 
 size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, const float *bounds, int dev, cudaStream_t s) {
@@ -744,28 +881,12 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
     }
     Scratch dist(n * sizeof(float), s);
     knn_mean_distances(in, n, k, hint_spacing, bounds, dist.as<float>(), dev, s);
-
-    Scratch partial(2 * ST_BLOCKS * sizeof(double), s);
-    launch("stats_kernel", s, 4 * (size_t)n, [&] { stats_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>()); });
-    double *h = static_cast<double *>(thread_pinned(2 * ST_BLOCKS * sizeof(double)));
-    CWCU_CHECK(cudaMemcpyAsync(h, partial.p, 2 * ST_BLOCKS * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
-    double sum = 0.0, sq = 0.0;
-    for (int b = 0; b < ST_BLOCKS; b++) {
-        sum += h[2 * b];
-        sq += h[2 * b + 1];
-    }
-    // ref: pcl statistical_outlier_removal.hpp -- mean, unbiased variance, threshold in double
-    const double dn = (double)n;
-    const double mean = sum / dn;
-    const double variance = (sq - sum * sum / dn) / (dn - 1.0);
-    const double stddev = std::sqrt(variance);
-    const double threshold = mean + (double)stddev_mul * stddev;
-
+    double sums[2];
+    distance_stats(dist.as<float>(), n, sums, s);
     Predicate p;
     p.kind = PredKind::DistanceAtMost;
     p.dist = dist.as<float>();
-    p.threshold = threshold;
+    p.threshold = outlier_threshold(sums[0], sums[1], (double)n, stddev_mul);
     return compact_points(in, n, out, p, dev, s);
 }
 

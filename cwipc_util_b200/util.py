@@ -150,6 +150,15 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
         "cwipc_cuda_pointcloud_device_ptr": ([cwipc_pointcloud_p], ctypes.c_void_p),
         "cwipc_cuda_knn_mean_distances": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t], ctypes.c_int),
         "cwipc_cuda_downsample_keys": ([cwipc_pointcloud_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t], ctypes.c_int),
+        "cwipc_cuda_octree_replay": ([cwipc_pointcloud_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_downsample_planned": ([cwipc_pointcloud_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p], cwipc_pointcloud_p),
+        "cwipc_cuda_from_device_points": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong], cwipc_pointcloud_p),
+        "cwipc_cuda_knn_query": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_knn_lists": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_knn_merge_lists": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_distance_stats": ([ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_outlier_threshold": ([ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float], ctypes.c_double),
+        "cwipc_cuda_filter_by_distance": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double], cwipc_pointcloud_p),
         "cwipc_cuda_timer_create": ([], ctypes.c_void_p),
         "cwipc_cuda_timer_destroy": ([ctypes.c_void_p], None),
         "cwipc_cuda_timer_start": ([ctypes.c_void_p], None),
@@ -476,3 +485,100 @@ def downsample_keys(pc: cwipc_pointcloud_wrapper, voxelsize: float) -> numpy.nda
     if rv < 0:
         raise CwipcError("cwipc_cuda_downsample_keys failed")
     return out
+
+
+# ---- partitioned clouds (one cloud over several GPUs; see slab.py) ----------------------------------
+class cwipc_cuda_octree_state(ctypes.Structure):
+    """include/cwipc_util_cuda.h: struct cwipc_cuda_octree_state"""
+    _fields_ = [("min", ctypes.c_double * 3), ("max", ctypes.c_double * 3), ("depth", ctypes.c_int32), ("valid", ctypes.c_int32)]
+
+    def to_array(self) -> numpy.ndarray:
+        return numpy.array(list(self.min) + list(self.max) + [float(self.depth), float(self.valid)], numpy.float64)
+
+    @classmethod
+    def from_array(cls, a) -> "cwipc_cuda_octree_state":
+        st = cls()
+        for i in range(3):
+            st.min[i] = float(a[i])
+            st.max[i] = float(a[3 + i])
+        st.depth = int(a[6])
+        st.valid = int(a[7])
+        return st
+
+
+def octree_replay(pc: cwipc_pointcloud_wrapper, cellsize: float, state: cwipc_cuda_octree_state):
+    """Insert pc's points into the octree box `state` (updated in place); returns pc's bounding box (6 floats)."""
+    bounds = numpy.zeros(6, numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_octree_replay(pc.as_cwipc_p(), cellsize, ctypes.addressof(state), bounds.ctypes.data)
+    if rv != 0:
+        raise CwipcError("cwipc_cuda_octree_replay failed")
+    return bounds
+
+
+def downsample_planned(pc: cwipc_pointcloud_wrapper, voxelsize: float, state: cwipc_cuda_octree_state, bounds) -> cwipc_pointcloud_wrapper:
+    b = numpy.ascontiguousarray(bounds, numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_downsample_planned(pc.as_cwipc_p(), voxelsize, ctypes.addressof(state), b.ctypes.data)
+    if not rv:
+        raise CwipcError("cwipc_cuda_downsample_planned failed")
+    return cwipc_pointcloud_wrapper(rv)
+
+
+def from_device_points(dev_ptr: int, npoint: int, timestamp: int) -> cwipc_pointcloud_wrapper:
+    rv = cwipc_util_dll_load().cwipc_cuda_from_device_points(dev_ptr, npoint, timestamp)
+    if not rv:
+        raise CwipcError("cwipc_cuda_from_device_points failed")
+    return cwipc_pointcloud_wrapper(rv)
+
+
+def pointcloud_device_ptr(pc: cwipc_pointcloud_wrapper) -> int:
+    return cwipc_util_dll_load().cwipc_cuda_pointcloud_device_ptr(pc.as_cwipc_p()) or 0
+
+
+def knn_query(pc: cwipc_pointcloud_wrapper, kNeighbors: int, nquery: int):
+    mean = numpy.zeros(nquery, numpy.float32)
+    kth2 = numpy.zeros(nquery, numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_knn_query(pc.as_cwipc_p(), kNeighbors, nquery, mean.ctypes.data, kth2.ctypes.data)
+    if rv < 0:
+        raise CwipcError("cwipc_cuda_knn_query failed")
+    return mean, kth2
+
+
+def knn_lists(pc: cwipc_pointcloud_wrapper, queries: numpy.ndarray, kNeighbors: int) -> numpy.ndarray:
+    q = numpy.ascontiguousarray(queries)
+    out = numpy.zeros((len(q), kNeighbors + 1), numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_knn_lists(pc.as_cwipc_p(), q.ctypes.data, len(q), kNeighbors, out.ctypes.data)
+    if rv < 0:
+        raise CwipcError("cwipc_cuda_knn_lists failed")
+    return out
+
+
+def knn_merge_lists(lists: numpy.ndarray, kNeighbors: int):
+    """lists[nlists][nq][k+1] -> (mean[nq], kth2[nq])"""
+    l = numpy.ascontiguousarray(lists, numpy.float32)
+    nlists, nq = l.shape[0], l.shape[1]
+    mean = numpy.zeros(nq, numpy.float32)
+    kth2 = numpy.zeros(nq, numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_knn_merge_lists(l.ctypes.data, nlists, nq, kNeighbors, mean.ctypes.data, kth2.ctypes.data)
+    if rv < 0:
+        raise CwipcError("cwipc_cuda_knn_merge_lists failed")
+    return mean, kth2
+
+
+def distance_stats(dist: numpy.ndarray):
+    d = numpy.ascontiguousarray(dist, numpy.float32)
+    sums = numpy.zeros(2, numpy.float64)
+    if cwipc_util_dll_load().cwipc_cuda_distance_stats(d.ctypes.data, len(d), sums.ctypes.data) != 0:
+        raise CwipcError("cwipc_cuda_distance_stats failed")
+    return float(sums[0]), float(sums[1])
+
+
+def outlier_threshold(total: float, sq: float, n: float, mul: float) -> float:
+    return cwipc_util_dll_load().cwipc_cuda_outlier_threshold(total, sq, n, mul)
+
+
+def filter_by_distance(pc: cwipc_pointcloud_wrapper, dist: numpy.ndarray, threshold: float) -> cwipc_pointcloud_wrapper:
+    d = numpy.ascontiguousarray(dist, numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_filter_by_distance(pc.as_cwipc_p(), d.ctypes.data, len(d), threshold)
+    if not rv:
+        raise CwipcError("cwipc_cuda_filter_by_distance failed")
+    return cwipc_pointcloud_wrapper(rv)

@@ -315,6 +315,36 @@ _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_tilefilter_masked(cwipc_pointclo
 _CWIPC_UTIL_EXPORT int cwipc_cuda_knn_mean_distances(cwipc_pointcloud *pc, int kNeighbors, float *dist, size_t ndist);
 /* Voxel keys of cwipc_downsample's key generation (one uint64 per input point, host buffer);
  * returns count or -1.  Diagnostic hook used by the parity tests. */
+/* ---- partitioned clouds: one cloud spread over several GPUs as x-slabs (BASELINE configs[3]) ----
+ * Building blocks only: every call is local to one GPU; the exchange steps between ranks (NCCL
+ * send/recv of boundary and halo points, all-reduce of the statistics) are made by the caller, see
+ * cwipc_util_b200/slab.py.  ref for the semantics being partitioned: src/cwipc_filters.cpp:89-278. */
+struct cwipc_cuda_octree_state { /* bounding box of pcl::octree::OctreePointCloud while points are inserted */
+    double min[3];
+    double max[3];
+    int32_t depth;
+    int32_t valid; /* 0: nothing inserted yet */
+};
+/* Insert this cloud's points (in order) into the octree box `state` (in/out); bounds = min xyz, max xyz of the cloud. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_octree_replay(cwipc_pointcloud *pc, float cellsize, struct cwipc_cuda_octree_state *state, float bounds[6]);
+/* cwipc_downsample of one part, with the octree box and the bounding box of the WHOLE cloud supplied. */
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_downsample_planned(cwipc_pointcloud *pc, float voxelsize, const struct cwipc_cuda_octree_state *state, const float bounds[6]);
+/* New cloud from npoint device-resident 16-byte points (device-to-device copy; e.g. an NCCL receive buffer). */
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_from_device_points(const void *dev_points, int npoint, uint64_t timestamp);
+/* First pass of cwipc_remove_outliers for the first nquery points against ALL points of the cloud (the rest
+ * being halo points): mean distance to the k nearest and the (k+1)-th smallest squared distance, nquery floats each. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_knn_query(cwipc_pointcloud *pc, int kNeighbors, int nquery, float *mean, float *kth2);
+/* The k+1 smallest squared distances (ascending, +inf padded) from nq arbitrary query points to the cloud: lists[nq][k+1]. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, int nq, int kNeighbors, float *lists);
+/* Merge lists[nlists][nq][k+1] (one list per part of the cloud) into the mean distance / (k+1)-th squared distance. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_knn_merge_lists(const float *lists, int nlists, int nq, int kNeighbors, float *mean, float *kth2);
+/* sums[0] = sum d, sums[1] = sum (float)(d*d), in double: the two numbers the parts all-reduce. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_distance_stats(const float *dist, size_t ndist, double sums[2]);
+/* mean + mul * stddev (unbiased) from the all-reduced sums, as pcl::StatisticalOutlierRemoval. */
+_CWIPC_UTIL_EXPORT double cwipc_cuda_outlier_threshold(double sum, double sq, double n, float stddevMulThresh);
+/* Second pass: keep point i iff !(dist[i] > threshold); order preserved. */
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_filter_by_distance(cwipc_pointcloud *pc, const float *dist, size_t ndist, double threshold);
+
 _CWIPC_UTIL_EXPORT int cwipc_cuda_downsample_keys(cwipc_pointcloud *pc, float voxelsize, uint64_t *keys, size_t nkeys);
 
 /* CUDA-event stopwatch on the calling thread's stream. */
