@@ -323,22 +323,28 @@ def run_ours(args):
     clocks = sampler.stop()
     dist_barrier(dist, torch)
 
-    # ---- roofline: a profiled pass of the same step (events around every kernel) ----
+    # ---- roofline: the same frames once more on ONE stream with events around every launch, so that the
+    # per-kernel durations are not inflated by the other streams' kernels sharing the SMs ----
+    state["stop"] = True
+    barrier.wait()
     prof = {}
     if rank == 0:
+        nprof = min(nframes, 12)
+        for f in range(2):                                # warm the main thread's stream, pools and workspace
+            o = workers[0].frame_chain(device_frames[f])
+            o.free()
+        cw.cuda_synchronize()
         lib.cwipc_cuda_profile_reset()
         lib.cwipc_cuda_profile_enable(1)
-        run_steps(workers, barrier, state, lib, "resident", 1)
+        for f in range(nprof):
+            o = workers[0].frame_chain(device_frames[f])
+            o.free()
+        cw.cuda_synchronize()
         lib.cwipc_cuda_profile_enable(0)
         need = lib.cwipc_cuda_profile_report(None, 0)
         buf = ctypes.create_string_buffer(need)
         lib.cwipc_cuda_profile_report(buf, need)
         prof = json.loads(buf.value.decode())
-    else:
-        run_steps(workers, barrier, state, lib, "resident", 1)
-
-    state["stop"] = True
-    barrier.wait()
 
     # ---- aggregate over ranks: time = max over ranks, work = sum ----
     total_ms = dist_reduce(dist, torch, sum(times), "MAX")
@@ -362,10 +368,18 @@ def run_ours(args):
         except Exception:
             pass
         step_kernel_ms = sum(r["total_ms"] for r in prof.values())
+        kernels = {}
+        for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"]):
+            gbs = v["bytes"] / max(v["total_ms"], 1e-9) / 1e6
+            kernels[k] = {"launches_per_frame": round(v["launches"] / nprof, 2), "us_per_launch": round(v["total_ms"] * 1e3 / max(1, v["launches"]), 2),
+                          "GBps": round(gbs, 1), "frac": round(gbs / peak, 4), "share": round(v["total_ms"] / step_kernel_ms, 3)}
         roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                     "traffic": traffic, "peak_source": peak_src, "launches": rec["launches"], "avg_launch_us": round(rec["total_ms"] * 1e3 / max(1, rec["launches"]), 2),
                     "algorithmic_bytes_per_launch": int(rec["bytes"] / max(1, rec["launches"])), "share_of_step_kernel_time": round(rec["total_ms"] / step_kernel_ms, 3),
-                    "kernels": {k: {"launches": v["launches"], "ms": round(v["total_ms"], 3), "GBps": round(v["bytes"] / max(v["total_ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])}}
+                    "how": f"{nprof} of the step's frames replayed on one stream, CUDA events around every launch (cwipc_cuda_profile_*)",
+                    "note": "the kNN kernels are instruction-issue bound (exact top-(k+1) selection over ~300 candidates per query), not HBM bound: "
+                            "their HBM fraction is reported as required, their issue utilisation is in profiles/",
+                    "kernels": kernels}
         # whole-op roofline on compulsory bytes: 16 B in + 16 B out per stage
         # downsample: 16 N in + 16 V out; remove_outliers: 16 V in + 16 M out   (per rank and step)
         compulsory = 16.0 * (nframes * POINTS_PER_FRAME + 2 * mid_points + out_points)
