@@ -7,6 +7,7 @@
 
 #include "kernels.hpp"
 #include "pointcloud.hpp"
+#include "radix_sort.hpp"
 
 using namespace cwcu;
 
@@ -407,6 +408,23 @@ cwipc_pointcloud *cwipc_cuda_filter_by_distance(cwipc_pointcloud *pc, const floa
         p.dist = d.as<float>();
         p.threshold = threshold;
         return compact_to_new(in, p, dev, s);
+    });
+}
+
+// Diagnostic: the library's stable LSD radix sort on bits [begin_bit, end_bit) of host words, in place.
+int cwipc_cuda_sort_u64(uint64_t *words, size_t n, int begin_bit, int end_bit) {
+    if (n > 0 && words == nullptr) return -1;
+    return guarded<int>("cwipc_cuda_sort_u64", -1, [&]() -> int {
+        if (n == 0) return 0;
+        const int dev = current_device();
+        DeviceGuard g(dev);
+        cudaStream_t s = thread_stream(dev);
+        Scratch a(n * sizeof(uint64_t), s), b(n * sizeof(uint64_t), s);
+        CWCU_CHECK(cudaMemcpyAsync(a.p, words, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+        const uint64_t *sorted = radix_sort_u64(a.as<uint64_t>(), b.as<uint64_t>(), n, begin_bit, end_bit, dev, s);
+        CWCU_CHECK(cudaMemcpyAsync(words, sorted, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        CWCU_CHECK(cudaStreamSynchronize(s));
+        return 0;
     });
 }
 

@@ -159,6 +159,7 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
         "cwipc_cuda_distance_stats": ([ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_outlier_threshold": ([ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float], ctypes.c_double),
         "cwipc_cuda_filter_by_distance": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double], cwipc_pointcloud_p),
+        "cwipc_cuda_sort_u64": ([ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int], ctypes.c_int),
         "cwipc_cuda_timer_create": ([], ctypes.c_void_p),
         "cwipc_cuda_timer_destroy": ([ctypes.c_void_p], None),
         "cwipc_cuda_timer_start": ([ctypes.c_void_p], None),
@@ -582,3 +583,11 @@ def filter_by_distance(pc: cwipc_pointcloud_wrapper, dist: numpy.ndarray, thresh
     if not rv:
         raise CwipcError("cwipc_cuda_filter_by_distance failed")
     return cwipc_pointcloud_wrapper(rv)
+
+
+def sort_u64(words: numpy.ndarray, begin_bit: int, end_bit: int) -> numpy.ndarray:
+    """Diagnostic: the library's stable radix sort on bits [begin_bit, end_bit) of a uint64 array."""
+    w = numpy.ascontiguousarray(words, numpy.uint64).copy()
+    if cwipc_util_dll_load().cwipc_cuda_sort_u64(w.ctypes.data, len(w), begin_bit, end_bit) != 0:
+        raise CwipcError("cwipc_cuda_sort_u64 failed")
+    return w

@@ -345,6 +345,8 @@ _CWIPC_UTIL_EXPORT double cwipc_cuda_outlier_threshold(double sum, double sq, do
 /* Second pass: keep point i iff !(dist[i] > threshold); order preserved. */
 _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_filter_by_distance(cwipc_pointcloud *pc, const float *dist, size_t ndist, double threshold);
 
+/* Diagnostic: stable LSD radix sort of n host words on bits [begin_bit, end_bit), in place (device sort). */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_sort_u64(uint64_t *words, size_t n, int begin_bit, int end_bit);
 _CWIPC_UTIL_EXPORT int cwipc_cuda_downsample_keys(cwipc_pointcloud *pc, float voxelsize, uint64_t *keys, size_t nkeys);
 
 /* CUDA-event stopwatch on the calling thread's stream. */

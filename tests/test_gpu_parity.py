@@ -511,3 +511,74 @@ def test_full_size_properties_8m(cw):
     vb = b.view(np.dtype((np.void, 16)))
     pos = np.flatnonzero(np.isin(va, vb))
     assert len(pos) >= len(b)
+
+
+# ======================================================================================================
+# building blocks: radix sort (both paths), workspace hygiene, concurrent callers
+# ======================================================================================================
+@pytest.mark.parametrize("n,begin,end", [(1, 3, 20), (2, 0, 1), (4096, 20, 45), (4097, 20, 38), (100000, 17, 42), (500000, 21, 30), (606209, 24, 51),
+                                          (700000, 20, 45), (3000000, 22, 49), (3000000, 0, 64), (50000, 16, 25), (50000, 16, 34)])
+def test_radix_sort_is_a_stable_sort_on_the_bit_range(cw, n, begin, end):
+    """<= 148 tiles of 4096 words go through the one-launch cooperative kernel (9-bit digits), larger inputs through onesweep."""
+    rng = np.random.default_rng(n + begin)
+    words = rng.integers(0, 2**63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    if n > 10:
+        words[: n // 3] &= np.uint64(0xFFFFFFFFFF)          # clustered high digits, as spatial keys are
+    got = cw.util.sort_u64(words, begin, end)
+    width = end - begin
+    field = (words >> np.uint64(begin)) & np.uint64((1 << width) - 1 if width < 64 else 0xFFFFFFFFFFFFFFFF)
+    want = words[np.argsort(field, kind="stable")]
+    assert np.array_equal(got, want)
+
+
+def test_downsample_heavy_voxels_and_contended_atomics(cw, orc):
+    """Hundreds of thousands of unordered points per voxel: every atomic of a warp lands on a handful of slots."""
+    pts = random_cloud(1500000, seed=3, extent=0.06)
+    for voxel in (0.05, -0.05):
+        d = cw.cwipc_downsample(upload(cw, pts), voxel)
+        want, cs, _, counts = orc.downsample(pts, voxel, 0.0, want_keys=False) if False else orc.downsample(pts, voxel, 0.0)
+        assert_points_close(download(d), want, cs)
+    assert d.count() <= 64
+
+
+def test_downsample_recovers_after_a_failed_call(cw, orc):
+    """A call that fails half way (coordinate out of range) must not leave the thread's hash workspace dirty."""
+    pts = synthetic.camera_cloud(50000, seed=4)
+    good, cs, _, _ = orc.downsample(pts, 0.01, 0.0)
+    assert_points_close(download(cw.cwipc_downsample(upload(cw, pts), 0.01)), good, cs)
+    bad = pts.copy()
+    bad["x"][1234] = 3.0e7
+    lib = cw.util.cwipc_util_dll_load()
+    assert not lib.cwipc_downsample(upload(cw, bad).as_cwipc_p(), 0.01)      # NULL + ERROR log
+    for _ in range(2):
+        assert_points_close(download(cw.cwipc_downsample(upload(cw, pts), 0.01)), good, cs)
+
+
+def test_concurrent_callers_get_the_sequential_results(cw):
+    """ctypes drops the GIL: 8 threads drive the GPU at once, each on its own stream and workspace."""
+    import threading
+    clouds = [synthetic.camera_cloud(60000 + 997 * i, seed=40 + i) for i in range(8)]
+
+    def chain(p):
+        pc = upload(cw, p, cellsize=0.002)
+        return download(cw.cwipc_remove_outliers(cw.cwipc_downsample(pc, 0.008), 20, 1.0, False))
+
+    want = [chain(p) for p in clouds]
+    got = [None] * len(clouds)
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(3):
+                got[i] = chain(clouds[i])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(clouds))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
