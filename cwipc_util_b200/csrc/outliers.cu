@@ -43,7 +43,7 @@ struct GridParams {
     float gmin[3];
     float inv_h;   // 1 / cell pitch
     float h;       // cell pitch
-    float rc;      // cover radius of the main pass, in cell pitches (<= 1.5)
+    float rc;      // cover radius of the main pass, in cell pitches (<= 1)
     int gdim[3];   // cells per axis at level 0
     int idxbits;
     int top_level; // level at which the whole grid is one cell
@@ -207,7 +207,7 @@ struct FarEntry {
 
 // ---- main pass: one warp per 32 consecutive (cell-ordered) queries, one lane per query ---------------
 // Queries that share a level-2 node (a 4x4x4 block of cells) are processed together: their candidate
-// set is every cell within rc pitches of their common bounding box (at most 8x8x8 cells).  Lane 0
+// set is every cell within rc pitches of their common bounding box (at most 6x6x6 cells).  Lane 0
 // streams the candidates' 16-byte records into a double-buffered shared-memory ring with TMA bulk
 // copies (one per contiguous cell range); every lane then scans the same records as broadcast 128-bit
 // shared loads.  Per lane, distances below the running (k+1)-th best are parked in a shared-memory
@@ -217,8 +217,9 @@ constexpr int KT_WARPS = 8;
 constexpr int KT_THREADS = KT_WARPS * 32;
 constexpr int KT_CH = 128;     // candidates per stage
 constexpr int KT_STAGES = 2;
-constexpr int KT_MAXR = 512;   // cells of the largest candidate box
+constexpr int KT_MAXR = 216;   // cells of the largest candidate box: 6x6x6 (a 4-cell group span + rc <= 1 on both sides)
 constexpr int KT_BUF = 16;     // parked distances per lane
+constexpr int KT_BLOCKS_PER_SM = 3; // register budget 85/thread: more resident warps hide the scan's latency
 
 struct __align__(128) KnnWarpSmem {
     Point16 cand[KT_STAGES][KT_CH]; // 4096 B
@@ -239,7 +240,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 template <int KCAP>
-__global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
+__global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
                                                                const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out, uint32_t nquery,
                                                                FarEntry *__restrict__ far_list, uint32_t *__restrict__ far_count) {
     extern __shared__ __align__(128) unsigned char knn_smem_raw[];
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(KT_THREADS) knn_tile_kernel(const cwipc_point 
                 const int cy0 = max((int)floorf(loy - rc), 0), cy1 = min((int)floorf(hiy + rc), gp.gdim[1] - 1);
                 const int cz0 = max((int)floorf(loz - rc), 0), cz1 = min((int)floorf(hiz + rc), gp.gdim[2] - 1);
                 const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1, nbz = cz1 - cz0 + 1;
-                const int nb = nbx * nby * nbz; // <= 8*8*8: the queries span at most 4 cells per axis and rc <= 1.5
+                const int nb = nbx * nby * nbz; // <= 6*6*6: the queries span at most 4 cells per axis and rc <= 1
                 const float rc2 = rc * rc;
                 // cells that overlap the queries' box first: their points tighten the running bound early,
                 // so most candidates of the surrounding shell fail the threshold test without being parked
@@ -682,7 +683,7 @@ struct GridPlan {
 // pass covers rc pitches around each query group.  The dense tables bound the number of cells.
 GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, float hint_spacing) {
     static const float pitch_factor = env_float("CWIPC_CUDA_KNN_PITCH", 1.0f, 0.05f, 20.f);
-    static const float rc = env_float("CWIPC_CUDA_KNN_RC", 1.0f, 0.25f, 1.5f);
+    static const float rc = env_float("CWIPC_CUDA_KNN_RC", 1.0f, 0.25f, 1.0f);
     GridPlan plan;
     GridParams &gp = plan.gp;
     memset(&gp, 0, sizeof(gp));
@@ -739,7 +740,7 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     static std::once_flag once[64];
     std::call_once(once[dev & 63], [&] { CWCU_CHECK(cudaFuncSetAttribute(knn_tile_kernel<KCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
     const size_t nitems = div_up(n, (size_t)32);
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nitems, (size_t)KT_WARPS), (size_t)sm_count(dev) * 2));
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nitems, (size_t)KT_WARPS), (size_t)sm_count(dev) * KT_BLOCKS_PER_SM));
     launch("knn_tile_kernel", s, 28 * (size_t)n, [&] {
         knn_tile_kernel<KCAP><<<grid, KT_THREADS, smem, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, (uint32_t)nquery, far_list, far_count);
     });
