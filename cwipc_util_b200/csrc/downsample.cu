@@ -289,6 +289,41 @@ __device__ __forceinline__ uint64_t spread3(uint32_t v) { // bit i -> bit 3i, v 
 }
 
 // Returns the sort key WITHOUT index bits; *bad is set when a coordinate is out of the supported range.
+// Leaf lookup tables (octree mode, at most 32 leaves per axis, i.e. clouds up to ~2000 voxels across): the
+// leaf index of a coordinate is a step function of the float32 value, so the host finds, with the very double
+// arithmetic of the generic path, the smallest float at which every step happens.  A point then costs a
+// 5-compare binary search per axis instead of double-precision subtract / multiply / floor / compare.
+constexpr int KT_LEAVES = 32;
+struct KeyTables {
+    float thr[3][KT_LEAVES];        // thr[a][m]: smallest float whose leaf index is first[a] + m + 1 (+inf beyond the last leaf)
+    int origin[3][KT_LEAVES];       // voxel-coordinate origin of leaf first[a] + m
+    uint64_t spread[3][KT_LEAVES];  // its Morton bits, already in the axis' position
+};
+
+__device__ __forceinline__ uint64_t voxel_key_tables(const Point16 &p, const KeyParams &kp, const KeyTables &tab, bool *bad) {
+    const float f[3] = {floorf(__fmul_rn(p.x, kp.inv)), floorf(__fmul_rn(p.y, kp.inv)), floorf(__fmul_rn(p.z, kp.inv))};
+    if (!(fabsf(f[0]) < 4194304.f && fabsf(f[1]) < 4194304.f && fabsf(f[2]) < 4194304.f)) {
+        *bad = true;
+        return 0;
+    }
+    const float c[3] = {p.x, p.y, p.z};
+    uint64_t morton = 0;
+    uint32_t w[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        int m = 0; // number of thresholds <= c[a]
+#pragma unroll
+        for (int step = KT_LEAVES / 2; step > 0; step >>= 1)
+            if (c[a] >= tab.thr[a][m + step - 1]) m += step;
+        const int wi = (int)f[a] - tab.origin[a][m];
+        if (wi < 0 || wi >= WL_RADIX) *bad = true;
+        w[a] = (uint32_t)min(max(wi, 0), WL_RADIX - 1);
+        morton |= tab.spread[a][m];
+    }
+    const uint64_t wlin = ((uint64_t)w[2] * WL_RADIX + w[1]) * WL_RADIX + w[0];
+    return (morton << WL_BITS) | wlin;
+}
+
 __device__ __forceinline__ uint64_t voxel_key(const Point16 &p, const KeyParams &kp, bool *bad) {
     const float f[3] = {floorf(__fmul_rn(p.x, kp.inv)), floorf(__fmul_rn(p.y, kp.inv)), floorf(__fmul_rn(p.z, kp.inv))};
     if (!(fabsf(f[0]) < 4194304.f && fabsf(f[1]) < 4194304.f && fabsf(f[2]) < 4194304.f)) {
@@ -370,8 +405,17 @@ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
 
 constexpr int VA_THREADS = 256;
 
-__global__ void __launch_bounds__(VA_THREADS) voxel_accumulate_kernel(const cwipc_point *__restrict__ pts, uint32_t n, KeyParams kp, double scale, VoxelSlot *__restrict__ table,
-                                                                       uint32_t slot_mask, int slotbits, uint64_t *__restrict__ list, TableHeader *__restrict__ header) {
+template <bool TABLES>
+__global__ void __launch_bounds__(VA_THREADS) voxel_accumulate_kernel(const cwipc_point *__restrict__ pts, uint32_t n, KeyParams kp, const __grid_constant__ KeyTables g_tab, float scale,
+                                                                       VoxelSlot *__restrict__ table, uint32_t slot_mask, int slotbits, uint64_t *__restrict__ list,
+                                                                       TableHeader *__restrict__ header) {
+    __shared__ KeyTables s_tab;
+    if (TABLES) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_tab); // kernel parameter (constant bank) -> shared
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_tab);
+        for (uint32_t i = threadIdx.x; i < sizeof(KeyTables) / 4; i += VA_THREADS) dst[i] = src[i];
+        __syncthreads();
+    }
     bool bad = false;
     const unsigned lane = lane_id();
     const unsigned le = lanemask_lt() | (1u << lane);
@@ -385,20 +429,24 @@ __global__ void __launch_bounds__(VA_THREADS) voxel_accumulate_kernel(const cwip
         uint32_t tl = 0;
         if (valid) {
             const Point16 p = ld_point_stream(pts, i);
-            key = voxel_key(p, kp, &bad);
-            fx = __double2ll_rn((double)p.x * scale);
-            fy = __double2ll_rn((double)p.y * scale);
-            fz = __double2ll_rn((double)p.z * scale);
+            key = TABLES ? voxel_key_tables(p, kp, s_tab, &bad) : voxel_key(p, kp, &bad);
+            // scale is a power of two: the float product is exact, so this is round(x * 2^s) like the double path
+            fx = __float2ll_rn(__fmul_rn(p.x, scale));
+            fy = __float2ll_rn(__fmul_rn(p.y, scale));
+            fz = __float2ll_rn(__fmul_rn(p.z, scale));
             rg = (unsigned long long)pt_r(p) | ((unsigned long long)pt_g(p) << 32);
             bn = (unsigned long long)pt_b(p) | (1ull << 32);
             tl = pt_tile(p);
         }
-        // runs of equal keys along the lanes -> inclusive segmented sums; the last lane of a run owns the total
+        // runs of equal keys along the lanes, cut every 8 lanes -> inclusive segmented sums in 3 shuffle steps;
+        // the last lane of a piece owns its total (longer runs cost one more set of atomics per 8 points)
         const uint64_t prev = __shfl_up_sync(FULL_MASK, key, 1);
-        const unsigned heads = __ballot_sync(FULL_MASK, lane == 0 || key != prev);
+        const unsigned run_heads = __ballot_sync(FULL_MASK, lane == 0 || key != prev);
+        const int run_start = 31 - __clz(run_heads & le);
+        const unsigned heads = __ballot_sync(FULL_MASK, (((int)lane - run_start) & 7) == 0);
         const int seg_start = 31 - __clz(heads & le);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < 8; o <<= 1) {
             const long long tx = __shfl_up_sync(FULL_MASK, fx, o), ty = __shfl_up_sync(FULL_MASK, fy, o), tz = __shfl_up_sync(FULL_MASK, fz, o);
             const unsigned long long trg = __shfl_up_sync(FULL_MASK, rg, o), tbn = __shfl_up_sync(FULL_MASK, bn, o);
             const uint32_t tt = __shfl_up_sync(FULL_MASK, tl, o);
@@ -510,6 +558,8 @@ struct Plan {
     float gmin[3] = {0, 0, 0}, gmax[3] = {0, 0, 0};
     size_t capacity = 0; // hash table slots (power of two)
     int slotbits = 0;
+    bool use_tables = false;
+    KeyTables tables;
 };
 
 // One launch + one readback: bounding box of the points and the octree box after inserting them in order
@@ -527,6 +577,48 @@ OctreeBox measure_box(const cwipc_point *pts, size_t n, float cellsize, bool oct
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
     CWCU_CHECK(cudaStreamSynchronize(s));
     return *h;
+}
+
+// host copies of the device formulas (IEEE double arithmetic on both sides)
+uint32_t host_leaf_index(float x, const KeyParams &kp, int a) { return (uint32_t)(((double)x - kp.omin[a]) / kp.res); }
+uint64_t host_spread3(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+// Leaf lookup tables for the accumulate kernel; false when an axis spans more than KT_LEAVES leaves.
+bool build_key_tables(const KeyParams &kp, const OctreeBox &ob, KeyTables &tab) {
+    for (int a = 0; a < 3; a++) {
+        if (!(ob.gmin[a] <= ob.gmax[a]) || (double)ob.gmin[a] < kp.omin[a]) return false;
+        const uint32_t first = host_leaf_index(ob.gmin[a], kp, a), last = host_leaf_index(ob.gmax[a], kp, a);
+        if (last < first || last - first + 1 > (uint32_t)KT_LEAVES || last >= (1u << kp.depth)) return false;
+        for (int m = 0; m < KT_LEAVES; m++) {
+            const uint32_t leaf = first + (uint32_t)m;
+            tab.thr[a][m] = INFINITY;
+            tab.origin[a][m] = 0;
+            tab.spread[a][m] = 0;
+            if (leaf > last) continue;
+            tab.origin[a][m] = (int)std::floor((kp.omin[a] + (double)leaf * kp.res) * kp.inv_cs) - 2;
+            tab.spread[a][m] = host_spread3(leaf) << (2 - a);
+            if (leaf == last) continue;
+            // smallest float whose leaf index is leaf + 1: start at the face, then walk to the exact step
+            float x = (float)(kp.omin[a] + (double)(leaf + 1) * kp.res);
+            for (int it = 0; it < 64 && host_leaf_index(x, kp, a) <= leaf; it++) x = std::nextafter(x, INFINITY);
+            for (int it = 0; it < 64; it++) {
+                const float below = std::nextafter(x, -INFINITY);
+                if (!((double)below >= kp.omin[a]) || host_leaf_index(below, kp, a) <= leaf) break;
+                x = below;
+            }
+            if (host_leaf_index(x, kp, a) != leaf + 1 || host_leaf_index(std::nextafter(x, -INFINITY), kp, a) != leaf) return false; // did not converge: generic path
+            tab.thr[a][m] = x;
+        }
+    }
+    return true;
 }
 
 // Key layout, hash-table size and limits from the measured (or supplied) boxes.
@@ -563,6 +655,7 @@ Plan derive_plan(const OctreeBox &ob, size_t n, float cellsize, bool octree_spli
         kp.inv_cs = 1.0 / (double)cellsize;
         kp.depth = ob.depth;
         plan.keybits = WL_BITS + 3 * ob.depth;
+        plan.use_tables = build_key_tables(kp, ob, plan.tables);
     } else {
         // ref: pcl VoxelGrid::applyFilter -- index-overflow guard, then min_b / div_b from the float bbox
         const float inv = kp.inv;
@@ -652,7 +745,12 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
     try {
         Scratch list(n * sizeof(uint64_t), s);
         launch("voxel_accumulate_kernel", s, 16 * (size_t)n, [&] {
-            voxel_accumulate_kernel<<<stream_grid(n, dev), VA_THREADS, 0, s>>>(in->d_pts, (uint32_t)n, kp, scale, table, (uint32_t)(capacity - 1), slotbits, list.as<uint64_t>(), header);
+            if (plan.use_tables)
+                voxel_accumulate_kernel<true><<<stream_grid(n, dev), VA_THREADS, 0, s>>>(in->d_pts, (uint32_t)n, kp, plan.tables, (float)scale, table, (uint32_t)(capacity - 1), slotbits,
+                                                                                          list.as<uint64_t>(), header);
+            else
+                voxel_accumulate_kernel<false><<<stream_grid(n, dev), VA_THREADS, 0, s>>>(in->d_pts, (uint32_t)n, kp, plan.tables, (float)scale, table, (uint32_t)(capacity - 1), slotbits,
+                                                                                           list.as<uint64_t>(), header);
         });
         uint32_t *h = static_cast<uint32_t *>(thread_pinned(2 * sizeof(uint32_t)));
         CWCU_CHECK(cudaMemcpyAsync(h, header, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -4,7 +4,7 @@ for st in downsample outliers; do for w in 4 8 16; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/stage_${st}_$w.json"))
-print("stage $st workers $w value",d["value"],"step_ms",d["step_ms"])
+print("stage $st workers $w value",d["value"],"ms_per_step",d["ms_per_step"])
 PY
 done; done
 for w in 12 16; do
@@ -12,6 +12,6 @@ for w in 12 16; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/both_$w.json"))
-print("both workers $w value",d["value"],"e2e",d["e2e"]["value"],"step_ms",d["step_ms"])
+print("both workers $w value",d["value"],"e2e",d["e2e"]["value"],"ms_per_step",d["ms_per_step"])
 PY
 done

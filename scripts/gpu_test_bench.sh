@@ -11,6 +11,6 @@ timeout 600 python bench.py --steps 5 --warmup 3 --cpu-frames 2 > gpurun_out/ben
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_${TAG}.json"))
-print("value",d["value"],"e2e",d["e2e"]["value"],"step_ms",d["step_ms"],"launches",d["gpu_launches"])
+print("value",d["value"],"e2e",d["e2e"]["value"],"ms_per_step",d["ms_per_step"],"launches",d["gpu_launches"])
 for n,v in d["roofline"]["kernels"].items(): print("  ",n,v)
 PY

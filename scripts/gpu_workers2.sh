@@ -3,6 +3,6 @@ for w in 8 12 16 24 32; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/w2.json"))
-print("workers $w frames 96 value",d["value"],"e2e",d["e2e"]["value"],"step_ms",d["step_ms"][:3])
+print("workers $w frames 96 value",d["value"],"e2e",d["e2e"]["value"],"ms_per_step",d["ms_per_step"])
 PY
 done

@@ -4,6 +4,6 @@ for w in 1 2 4 8 16; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/sweep_w$w.json"))
-print("workers",$w,"value",d["value"],"e2e",d["e2e"]["value"],"step_ms",d["step_ms"],"e2e_ms",d["e2e_step_ms"])
+print("workers",$w,"value",d["value"],"e2e",d["e2e"]["value"],"ms_per_step",d["ms_per_step"])
 PY
 done
