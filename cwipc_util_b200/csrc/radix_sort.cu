@@ -11,6 +11,7 @@
 #include "radix_sort.hpp"
 
 #include <cooperative_groups.h>
+#include <cstring>
 #include <mutex>
 
 #include "device_utils.cuh"
@@ -209,10 +210,26 @@ constexpr size_t RF_SMEM_BYTES = RS_TILE * sizeof(uint64_t) + (size_t)(RS_WARPS 
 // pass widths: as few passes as RF_BITS allows, evenly wide
 __host__ __device__ __forceinline__ int fused_passes(int bits) { return (bits + RF_BITS - 1) / RF_BITS; }
 
+// Grid barrier for the cooperative launch (all blocks are co-resident): one arrival per block on a monotonic
+// counter, acquire-spin until the k-th multiple of the block count.  Lighter than cg::grid.sync(), which costs
+// several microseconds per call here -- more than a whole pass over a 4096-key tile.
+__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        uint32_t seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__restrict__ a, uint64_t *__restrict__ b, uint32_t n, int begin_bit, int end_bit,
-                                                                  uint32_t *__restrict__ tile_hist /* [2][ntiles][RF_BINS] */) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+                                                                  uint32_t *__restrict__ tile_hist /* [2][ntiles][RF_BINS] */, uint32_t *__restrict__ sync_words /* [2], zero */) {
+    uint32_t nbarriers = 0;
     extern __shared__ __align__(16) unsigned char rf_smem[]; // RF_SMEM_BYTES, above the 48 KB static limit
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(rf_smem);                               // [RS_TILE]
     uint32_t(*s_warp_hist)[RF_BINS] = reinterpret_cast<uint32_t(*)[RF_BINS]>(s_keys + RS_TILE); // [RS_WARPS][RF_BINS]
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
             count[j] = c;
             hist[(size_t)tile * RF_BINS + d] = c;
         }
-        grid.sync();
+        grid_barrier(sync_words, ++nbarriers * ntiles);
 
         // keys with my digits in earlier tiles and in all tiles
         uint32_t before_tiles[RF_DPT], total[RF_DPT];
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
         for (uint32_t t = 0; t < ntiles; t++) {
 #pragma unroll
             for (int j = 0; j < RF_DPT; j++) {
-                const uint32_t c = hist[(size_t)t * RF_BINS + threadIdx.x * RF_DPT + j];
+                const uint32_t c = __ldcg(hist + (size_t)t * RF_BINS + threadIdx.x * RF_DPT + j);
                 if (t < tile) before_tiles[j] += c;
                 total[j] += c;
             }
@@ -341,12 +358,179 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
                 dst[s_bin_out[digit_of(k, shift, mask)] + p] = k;
             }
         }
-        grid.sync();
+        grid_barrier(sync_words, ++nbarriers * ntiles);
         uint64_t *t = src;
         src = dst;
         dst = t;
         shift += bits;
     }
+    // leave the two words zero for the next launch: the last block to get here resets them (nobody spins any more)
+    if (threadIdx.x == 0 && atomicAdd(sync_words + 1, 1u) == ntiles - 1) {
+        sync_words[0] = 0;
+        sync_words[1] = 0;
+    }
+}
+
+// ---- up to ~98 K words: the whole sort inside ONE thread-block cluster, keys in distributed shared memory ---
+// A cluster of up to 8 CTAs (one per SM, co-scheduled by the hardware) holds the keys in registers between
+// ranking and scatter and in shared memory between passes.  Per pass: warp match_any ranking, per-CTA digit
+// counts, cluster barrier, every CTA reads the other CTAs' counts through DSMEM, keys are scattered straight
+// into the destination CTA's shared memory (st.shared::cluster), cluster barrier.  No global-memory traffic and
+// no grid barrier between passes: a cluster barrier costs a few hundred cycles, and the launch is an ordinary one.
+constexpr int RC_THREADS = 512;
+constexpr int RC_WARPS = RC_THREADS / 32;
+constexpr int RC_BITS = 9;
+constexpr int RC_BINS = 1 << RC_BITS; // == RC_THREADS: one digit per thread
+constexpr int RC_MAX_CTAS = 8;        // portable cluster size.  16-CTA clusters halve the single-stream latency of a 47 K-word
+                                      // sort (31 vs 52 us) but lower the multi-stream throughput: a GPC rarely has 12 idle SMs
+
+template <int IPT>
+constexpr size_t rc_smem_bytes() { return (size_t)RC_THREADS * IPT * sizeof(uint64_t) + (size_t)(RC_WARPS + 2) * RC_BINS * sizeof(uint32_t) + RC_WARPS * sizeof(uint32_t); }
+
+template <int IPT>
+__global__ void __launch_bounds__(RC_THREADS, 1) radix_cluster_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint32_t n, int begin_bit, int end_bit) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t nctas = cluster.num_blocks(), cta = cluster.block_rank();
+    constexpr uint32_t CAP = RC_THREADS * IPT; // words per CTA
+    extern __shared__ __align__(16) unsigned char rc_smem[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(rc_smem);                                       // [CAP] this CTA's words between passes
+    uint32_t(*warp_hist)[RC_BINS] = reinterpret_cast<uint32_t(*)[RC_BINS]>(buf + CAP);           // [RC_WARPS][RC_BINS]
+    uint32_t *cta_hist = &warp_hist[RC_WARPS][0];                                                // [RC_BINS] read by the other CTAs
+    uint32_t *digit_off = cta_hist + RC_BINS;                                                    // [RC_BINS]
+    uint32_t *s_scan = digit_off + RC_BINS;                                                      // [RC_WARPS]
+
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t local_base = warp * (32 * IPT);
+    const uint32_t warp_base = cta * CAP + local_base;
+    const uint32_t d = threadIdx.x;
+
+    uint64_t key[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+        const uint32_t idx = warp_base + i * 32 + lane;
+        key[i] = idx < n ? in[idx] : ~0ull;
+    }
+    const int npasses = (end_bit - begin_bit + RC_BITS - 1) / RC_BITS;
+    int shift = begin_bit;
+    for (int pass = 0; pass < npasses; pass++) {
+        const int bits = (end_bit - shift + (npasses - pass) - 1) / (npasses - pass);
+        const uint32_t mask = (1u << bits) - 1u;
+        const bool last = pass + 1 == npasses;
+#pragma unroll
+        for (int w = 0; w < RC_WARPS; w++) warp_hist[w][d] = 0;
+        __syncthreads();
+
+        uint32_t rank[IPT];
+        uint32_t *my_hist = warp_hist[warp];
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const uint32_t idx = warp_base + i * 32 + lane;
+            const bool valid = idx < n;
+            const uint32_t dg = valid ? digit_of(key[i], shift, mask) : 0xffffu;
+            const unsigned peers = __match_any_sync(FULL_MASK, dg);
+            const int leader = __ffs(peers) - 1;
+            uint32_t before = 0;
+            if ((int)lane == leader && valid) {
+                before = my_hist[dg];
+                my_hist[dg] = before + __popc(peers);
+            }
+            before = __shfl_sync(FULL_MASK, before, leader);
+            rank[i] = before + __popc(peers & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // digit d: offsets across this CTA's warps, CTA count
+        uint32_t count = 0;
+#pragma unroll
+        for (int w = 0; w < RC_WARPS; w++) {
+            const uint32_t v = warp_hist[w][d];
+            warp_hist[w][d] = count;
+            count += v;
+        }
+        cta_hist[d] = count;
+        cluster.sync();
+
+        // counts of digit d in the CTAs before this one and in all CTAs, read through distributed shared memory
+        uint32_t before_ctas = 0, total = 0;
+        for (uint32_t cc = 0; cc < nctas; cc++) {
+            const uint32_t v = *cluster.map_shared_rank(&cta_hist[d], cc);
+            if (cc < cta) before_ctas += v;
+            total += v;
+        }
+        {
+            const uint32_t incl = warp_inclusive_scan(total);
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            uint32_t off = incl - total;
+            for (int w = 0; w < (int)warp; w++) off += s_scan[w];
+            digit_off[d] = off + before_ctas; // position of this CTA's first word with digit d
+        }
+        __syncthreads();
+
+        // scatter: the last pass goes to global memory, the others into the owning CTA's shared memory
+#pragma unroll
+        for (int i = 0; i < IPT; i++) {
+            const uint32_t idx = warp_base + i * 32 + lane;
+            if (idx < n) {
+                const uint32_t dg = digit_of(key[i], shift, mask);
+                const uint32_t pos = digit_off[dg] + my_hist[dg] + rank[i];
+                if (last) {
+                    out[pos] = key[i];
+                } else {
+                    *cluster.map_shared_rank(&buf[pos % CAP], pos / CAP) = key[i];
+                }
+            }
+        }
+        cluster.sync(); // remote stores have landed; nobody reads cta_hist any more (and no CTA exits early)
+        if (!last) {
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                const uint32_t idx = warp_base + i * 32 + lane;
+                key[i] = idx < n ? buf[local_base + i * 32 + lane] : ~0ull;
+            }
+        }
+        shift += bits;
+    }
+}
+
+template <int IPT>
+bool launch_cluster_sort(const uint64_t *in, uint64_t *out, size_t n, int begin_bit, int end_bit, int dev, cudaStream_t s) {
+    static int ok[64]; // 0 unknown, 1 usable, -1 not usable on this device
+    static std::once_flag once[64];
+    std::call_once(once[dev & 63], [&] {
+        cudaError_t e = cudaFuncSetAttribute(radix_cluster_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rc_smem_bytes<IPT>());
+        ok[dev & 63] = (e == cudaSuccess) ? 1 : -1;
+        if (e != cudaSuccess) (void)cudaGetLastError();
+    });
+    if (ok[dev & 63] != 1) return false;
+    const size_t cap = (size_t)RC_THREADS * IPT;
+    const unsigned nctas = (unsigned)div_up(n, cap);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nctas);
+    cfg.blockDim = dim3(RC_THREADS);
+    cfg.dynamicSmemBytes = rc_smem_bytes<IPT>();
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint32_t n32 = (uint32_t)n;
+    bool launched = true;
+    launch("radix_cluster_kernel", s, 16 * n, [&] {
+        cudaError_t e = cudaLaunchKernelEx(&cfg, radix_cluster_kernel<IPT>, in, out, n32, begin_bit, end_bit);
+        if (e != cudaSuccess) { // e.g. no GPC with enough free SMs configuration: fall back to the cooperative kernel
+            (void)cudaGetLastError();
+            launched = false;
+        }
+    });
+    return launched;
 }
 
 int fused_tile_limit(int dev) {
@@ -371,12 +555,19 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
     if (npasses > RS_MAX_PASSES) throw CudaError{cudaErrorInvalidValue, "radix_sort_u64: bit range too wide"};
     const size_t ntiles = div_up(n, RS_TILE);
 
+    // one cluster of <= 8 CTAs sorts up to 8 x 512 x 24 words entirely in distributed shared memory
+    if (n <= (size_t)RC_MAX_CTAS * RC_THREADS * 8) {
+        if (launch_cluster_sort<8>(a, b, n, begin_bit, end_bit, dev, s)) return b;
+    } else if (n <= (size_t)RC_MAX_CTAS * RC_THREADS * 24) {
+        if (launch_cluster_sort<24>(a, b, n, begin_bit, end_bit, dev, s)) return b;
+    }
     if ((int)ntiles <= fused_tile_limit(dev)) {
         const int fpasses = fused_passes(end_bit - begin_bit);
         Scratch hist(2 * ntiles * RF_BINS * sizeof(uint32_t), s);
         uint32_t *tile_hist = hist.as<uint32_t>();
         uint32_t n32 = (uint32_t)n;
-        void *args[] = {&a, &b, &n32, &begin_bit, &end_bit, &tile_hist};
+        uint32_t *sync_words = static_cast<uint32_t *>(thread_zeroed(dev, 64, s)) + 4; // words 4,5 of the zeroed workspace header
+        void *args[] = {&a, &b, &n32, &begin_bit, &end_bit, &tile_hist, &sync_words};
         launch("radix_fused_kernel", s, 16 * (size_t)n * fpasses, [&] {
             CWCU_CHECK(cudaLaunchCooperativeKernel((const void *)radix_fused_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, RF_SMEM_BYTES, s));
         });

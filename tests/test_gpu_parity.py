@@ -517,9 +517,11 @@ def test_full_size_properties_8m(cw):
 # building blocks: radix sort (both paths), workspace hygiene, concurrent callers
 # ======================================================================================================
 @pytest.mark.parametrize("n,begin,end", [(1, 3, 20), (2, 0, 1), (4096, 20, 45), (4097, 20, 38), (100000, 17, 42), (500000, 21, 30), (606209, 24, 51),
-                                          (700000, 20, 45), (3000000, 22, 49), (3000000, 0, 64), (50000, 16, 25), (50000, 16, 34)])
+                                          (700000, 20, 45), (3000000, 22, 49), (3000000, 0, 64), (50000, 16, 25), (50000, 16, 34),
+                                          (32768, 16, 41), (32769, 16, 41), (98304, 17, 35), (98305, 17, 35), (12289, 0, 9), (70001, 30, 31)])
 def test_radix_sort_is_a_stable_sort_on_the_bit_range(cw, n, begin, end):
-    """<= 148 tiles of 4096 words go through the one-launch cooperative kernel (9-bit digits), larger inputs through onesweep."""
+    """<= 98304 words: one thread-block cluster, keys in distributed shared memory; <= 148 tiles of 4096 words: the one-launch
+    cooperative kernel; larger inputs: onesweep."""
     rng = np.random.default_rng(n + begin)
     words = rng.integers(0, 2**63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
     if n > 10:
