@@ -39,7 +39,7 @@ POINTS_PER_FRAME = 1000 * 1000
 VOXEL = 0.01
 K, STDDEV = 30, 1.0
 FRAMES_PER_GPU = 30          # 240 frames / 8 GPUs
-WORKERS = 10                 # host threads (one CUDA stream each) feeding one GPU; divides the 30 frames of a step
+WORKERS = 15                 # host threads (one CUDA stream each) feeding one GPU; divides the 30 frames of a step
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -269,7 +269,17 @@ def cpu_baseline_sample(frames, nframes):
 
 
 def run_ours(args):
+    # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version banner)
+    # is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     world, rank, local, dist, torch = dist_setup(args)
+    # Host threads: each worker spends most of its time waiting for a count readback; the library polls briefly and
+    # then naps between polls (csrc/runtime.cu: stream_sync), so 15 threads per GPU also work on 4 cores per GPU.
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if args.workers <= 0:
+        args.workers = WORKERS
     import cwipc_util_b200 as cw
     from cwipc_util_b200 import synthetic
     lib = cw.util.cwipc_util_dll_load()
@@ -398,7 +408,7 @@ def run_ours(args):
         "dtype": "f32 keys/distances, int64 fixed-point sums, f64 statistics", "data": "synthetic",
         "config": {"workload": "configs[4]: 1M-point 4-camera synthetic frames, per frame cwipc_downsample(0.01) -> cwipc_remove_outliers(30,1.0,perTile=False); "
                                f"{nframes} frames per GPU per step, frame-sharded, no collective", "points_per_frame": POINTS_PER_FRAME, "frames_per_gpu_per_step": nframes,
-                   "host_threads_per_gpu": nworkers, "l2": f"inputs larger than L2 ({nframes} x 16 MB per GPU per step, each frame touched once per step)",
+                   "host_threads_per_gpu": nworkers, "host_cores": cores, "host_wait": "poll %s us then nap %s us" % (os.environ.get("CWIPC_CUDA_SPIN_US", "20"), os.environ.get("CWIPC_CUDA_SLEEP_US", "20")), "l2": f"inputs larger than L2 ({nframes} x 16 MB per GPU per step, each frame touched once per step)",
                    "parallelism": f"frames x{world}"},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpoints/s", "h2d_bytes_per_step": points_per_step * 16, "d2h_bytes_per_step": int(d2h_all / max(1, args.steps)),
                 "ms_per_step": round(total_e2e_ms / args.steps, 3)},
@@ -410,7 +420,8 @@ def run_ours(args):
         "out_points_per_step": int(out_points),
         "timed_region_ms": round(total_ms, 3), "e2e_timed_region_ms": round(total_e2e_ms, 3),
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 # --------------------------------------------------------------------------------------------------
@@ -467,7 +478,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
-    ap.add_argument("--workers", type=int, default=WORKERS)
+    ap.add_argument("--workers", type=int, default=0, help="host threads per GPU (0 = choose from the core count)")
     ap.add_argument("--cpu-frames", type=int, default=24)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -238,7 +238,7 @@ int cwipc_cuda_synchronize(void) {
     return guarded<int>("cwipc_cuda_synchronize", -1, [&] {
         const int dev = current_device();
         DeviceGuard g(dev);
-        CWCU_CHECK(cudaStreamSynchronize(thread_stream(dev)));
+        stream_sync(thread_stream(dev));
         return 0;
     });
 }

@@ -575,7 +575,7 @@ OctreeBox measure_box(const cwipc_point *pts, size_t n, float cellsize, bool oct
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
     return *h;
 }
 
@@ -754,7 +754,7 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
         });
         uint32_t *h = static_cast<uint32_t *>(thread_pinned(2 * sizeof(uint32_t)));
         CWCU_CHECK(cudaMemcpyAsync(h, header, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         const size_t v = h[0];
         if (h[1] != 0) {
             thread_zeroed_invalidate(dev);
@@ -853,7 +853,7 @@ void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], 
     });
     OctreeBox *h = static_cast<OctreeBox *>(thread_pinned(sizeof(OctreeBox)));
     CWCU_CHECK(cudaMemcpyAsync(h, box.p, sizeof(OctreeBox), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
     for (int a = 0; a < 3; a++) {
         gmin[a] = h->gmin[a];
         gmax[a] = h->gmax[a];
@@ -870,7 +870,7 @@ void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_s
     CWCU_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
     launch("voxel_keygen_kernel", s, 24 * (size_t)n, [&] { voxel_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in->d_pts, (uint32_t)n, plan.kp, keys.as<uint64_t>(), 0, flag.as<uint32_t>()); });
     CWCU_CHECK(cudaMemcpyAsync(host_keys, keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
 }
 
 } // namespace cwcu

@@ -239,7 +239,7 @@ int cwipc_cuda_knn_mean_distances(cwipc_pointcloud *pc, int kNeighbors, float *d
         knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), bounds_of(*in, box), d.as<float>(), in->dev, s);
         CWCU_CHECK(cudaMemcpyAsync(dist, d.p, in->count * sizeof(float), cudaMemcpyDeviceToHost, s));
         in->release_after_read(s);
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return (int)in->count;
     });
 }
@@ -319,7 +319,7 @@ cwipc_pointcloud *cwipc_cuda_from_device_points(const void *dev_points, int npoi
         out->count = (size_t)npoint;
         if (npoint) CWCU_CHECK(cudaMemcpyAsync(out->d_pts, dev_points, (size_t)npoint * sizeof(cwipc_point), cudaMemcpyDefault, s));
         out->mark_ready();
-        CWCU_CHECK(cudaStreamSynchronize(s)); // the caller may reuse its buffer on return
+        stream_sync(s); // the caller may reuse its buffer on return
         return new DevicePointcloud(out, timestamp, 0.f);
     });
 }
@@ -339,7 +339,7 @@ int cwipc_cuda_knn_query(cwipc_pointcloud *pc, int kNeighbors, int nquery, float
         CWCU_CHECK(cudaMemcpyAsync(mean, d.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (kth2) CWCU_CHECK(cudaMemcpyAsync(kth2, kth.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToHost, s));
         in->release_after_read(s);
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return nquery;
     });
 }
@@ -360,7 +360,7 @@ int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries
         knn_lists(in->d_pts, in->count, q.as<cwipc_point>(), (size_t)nq, kNeighbors, pc->cellsize(), bounds_of(*in, box), l.as<float>(), in->dev, s);
         CWCU_CHECK(cudaMemcpyAsync(lists, l.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, s));
         in->release_after_read(s);
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return nq;
     });
 }
@@ -378,7 +378,7 @@ int cwipc_cuda_knn_merge_lists(const float *lists, int nlists, int nq, int kNeig
         knn_merge_lists(l.as<float>(), (size_t)nlists, (size_t)nq, kNeighbors, m.as<float>(), kt.as<float>(), s);
         CWCU_CHECK(cudaMemcpyAsync(mean, m.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (kth2) CWCU_CHECK(cudaMemcpyAsync(kth2, kt.p, (size_t)nq * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return nq;
     });
 }
@@ -423,7 +423,7 @@ int cwipc_cuda_sort_u64(uint64_t *words, size_t n, int begin_bit, int end_bit) {
         CWCU_CHECK(cudaMemcpyAsync(a.p, words, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
         const uint64_t *sorted = radix_sort_u64(a.as<uint64_t>(), b.as<uint64_t>(), n, begin_bit, end_bit, dev, s);
         CWCU_CHECK(cudaMemcpyAsync(words, sorted, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return 0;
     });
 }

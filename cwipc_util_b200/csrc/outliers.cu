@@ -827,7 +827,7 @@ void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, si
     if (n == 0) { // nothing to answer with: every list is all +inf (0x7f800000)
         std::vector<float> inf(nq * (size_t)kk, INFINITY);
         CWCU_CHECK(cudaMemcpyAsync(d_lists, inf.data(), inf.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return;
     }
     KnnIndex ix;
@@ -856,7 +856,7 @@ void distance_stats(const float *d_dist, size_t n, double out[2], cudaStream_t s
     launch("stats_kernel", s, 4 * n, [&] { stats_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(d_dist, (uint32_t)n, partial.as<double>()); });
     double *h = static_cast<double *>(thread_pinned(2 * ST_BLOCKS * sizeof(double)));
     CWCU_CHECK(cudaMemcpyAsync(h, partial.p, 2 * ST_BLOCKS * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
     for (int b = 0; b < ST_BLOCKS; b++) {
         out[0] += h[2 * b];
         out[1] += h[2 * b + 1];

@@ -62,7 +62,7 @@ DevicePointcloud *DevicePointcloud::from_host(const cwipc_point *points, size_t 
     store->mark_ready();
     // Pageable source memory has already been staged by the driver when cudaMemcpyAsync returns;
     // page-locked memory is read by the DMA engine later, so wait unless the caller opted out.
-    if (sync && npoint && is_pinned_host(points)) CWCU_CHECK(cudaStreamSynchronize(s));
+    if (sync && npoint && is_pinned_host(points)) stream_sync(s);
     return new DevicePointcloud(store, timestamp, 0.f);
 }
 
@@ -132,7 +132,7 @@ int DevicePointcloud::copy_uncompressed(struct cwipc_point *pointbuf, size_t siz
         st->acquire_for_read(s);
         CWCU_CHECK(cudaMemcpyAsync(pointbuf, st->d_pts, need, cudaMemcpyDeviceToHost, s));
         st->release_after_read(s);
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return (int)st->count;
     });
 }
@@ -185,7 +185,7 @@ StoragePtr storage_of(cwipc_pointcloud *pc, const char *who) {
         store->count = n;
         if (n) CWCU_CHECK(cudaMemcpyAsync(store->d_pts, host.data(), bytes, cudaMemcpyHostToDevice, s));
         store->mark_ready();
-        CWCU_CHECK(cudaStreamSynchronize(s));
+        stream_sync(s);
         return store;
     });
 }

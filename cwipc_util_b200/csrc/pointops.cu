@@ -116,7 +116,7 @@ size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred,
     });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
     profile_add_bytes("compact_kernel", 16 * (size_t)*h); // survivors written
     return *h;
 }
@@ -229,7 +229,7 @@ float min_distance_to_first(const cwipc_point *in, size_t n, cudaStream_t s) {
     launch("min_dist2_kernel", s, 16 * (size_t)n, [&] { min_dist2_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, scratch.as<uint32_t>()); });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, scratch.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
     float d2;
     memcpy(&d2, h, sizeof(float));
     if (!(d2 < __builtin_inff())) return 0.f; // no finite distance found
@@ -245,7 +245,7 @@ std::vector<int> tiles_in_first_appearance_order(const cwipc_point *in, size_t n
     launch("first_tile_kernel", s, 16 * (size_t)n, [&] { first_tile_kernel<<<grid, 256, 0, s>>>(in, (uint32_t)n, scratch.as<uint32_t>()); });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(256 * sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, scratch.p, 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CWCU_CHECK(cudaStreamSynchronize(s));
+    stream_sync(s);
     std::vector<std::pair<uint32_t, int>> found;
     for (int t = 0; t < 256; t++)
         if (h[t] != 0xffffffffu) found.emplace_back(h[t], t);

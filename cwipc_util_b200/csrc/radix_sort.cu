@@ -120,13 +120,10 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(const uint64
         const bool valid = idx < n;
         const uint32_t d = valid ? digit_of(key[i], shift, mask) : 0x100u;
         const unsigned peers = __match_any_sync(FULL_MASK, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t before = 0;
-        if ((int)lane == leader && valid) {
-            before = my_hist[d];
-            my_hist[d] = before + __popc(peers);
-        }
-        before = __shfl_sync(FULL_MASK, before, leader);
+        // every peer reads the running count (one broadcast per digit), the lowest one bumps it: no shuffle on the chain
+        const uint32_t before = valid ? my_hist[d] : 0u;
+        __syncwarp();
+        if (valid && (peers & lt) == 0u) my_hist[d] = before + __popc(peers);
         rank[i] = before + __popc(peers & lt);
         __syncwarp();
     }
@@ -269,13 +266,10 @@ __global__ void __launch_bounds__(RS_THREADS) radix_fused_kernel(uint64_t *__res
             const bool valid = idx < n;
             const uint32_t dg = valid ? digit_of(key[i], shift, mask) : 0xffffu;
             const unsigned peers = __match_any_sync(FULL_MASK, dg);
-            const int leader = __ffs(peers) - 1;
-            uint32_t before = 0;
-            if ((int)lane == leader && valid) {
-                before = my_hist[dg];
-                my_hist[dg] = before + __popc(peers);
-            }
-            before = __shfl_sync(FULL_MASK, before, leader);
+            // every peer reads the running count (one broadcast per digit), the lowest one bumps it: no shuffle on the chain
+            const uint32_t before = valid ? my_hist[dg] : 0u;
+            __syncwarp();
+            if (valid && (peers & lt) == 0u) my_hist[dg] = before + __popc(peers);
             rank[i] = before + __popc(peers & lt);
             __syncwarp();
         }
@@ -430,13 +424,10 @@ __global__ void __launch_bounds__(RC_THREADS, 1) radix_cluster_kernel(const uint
             const bool valid = idx < n;
             const uint32_t dg = valid ? digit_of(key[i], shift, mask) : 0xffffu;
             const unsigned peers = __match_any_sync(FULL_MASK, dg);
-            const int leader = __ffs(peers) - 1;
-            uint32_t before = 0;
-            if ((int)lane == leader && valid) {
-                before = my_hist[dg];
-                my_hist[dg] = before + __popc(peers);
-            }
-            before = __shfl_sync(FULL_MASK, before, leader);
+            // every peer reads the running count (one broadcast per digit), the lowest one bumps it: no shuffle on the chain
+            const uint32_t before = valid ? my_hist[dg] : 0u;
+            __syncwarp();
+            if (valid && (peers & lt) == 0u) my_hist[dg] = before + __popc(peers);
             rank[i] = before + __popc(peers & lt);
             __syncwarp();
         }

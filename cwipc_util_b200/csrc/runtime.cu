@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <sstream>
 
@@ -69,6 +70,7 @@ struct ThreadState {
     std::vector<cudaStream_t> streams; // per device
     void *pinned = nullptr;
     size_t pinned_size = 0;
+    cudaEvent_t sync_event[64] = {nullptr}; // per device, created with cudaEventBlockingSync
     struct Zeroed {
         void *p = nullptr;
         size_t size = 0;
@@ -221,6 +223,44 @@ void *thread_zeroed(int dev, size_t bytes, cudaStream_t s) {
 
 void thread_zeroed_invalidate(int dev) {
     if ((int)t_state.zeroed.size() > dev) t_state.zeroed[dev].dirty = true;
+}
+
+void stream_sync(cudaStream_t s) {
+    static const long spin_ns = [] {
+        const char *e = getenv("CWIPC_CUDA_SPIN_US");
+        return (e && *e) ? atol(e) * 1000L : 20000L;
+    }();
+    static const long sleep_ns = [] { // > 0: after the polling budget, poll every sleep_ns instead of blocking in the driver
+        const char *e = getenv("CWIPC_CUDA_SLEEP_US");
+        return (e && *e) ? atol(e) * 1000L : 20000L;
+    }();
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    cudaEvent_t &ev = t_state.sync_event[dev & 63];
+    if (!ev) CWCU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    CWCU_CHECK(cudaEventRecord(ev, s));
+    timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    while (true) {
+        const cudaError_t q = cudaEventQuery(ev);
+        if (q == cudaSuccess) return;
+        if (q != cudaErrorNotReady) throw_cuda(q, "cudaEventQuery(sync)", __FILE__, __LINE__);
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if ((t1.tv_sec - t0.tv_sec) * 1000000000L + (t1.tv_nsec - t0.tv_nsec) >= spin_ns) break;
+    }
+    if (sleep_ns > 0) {
+        // few cores, many waiting threads: give the core away between polls (a blocking wait in the driver wakes up
+        // through an interrupt, which is slow in virtual machines)
+        const timespec nap = {0, sleep_ns};
+        while (true) {
+            nanosleep(&nap, nullptr);
+            const cudaError_t q = cudaEventQuery(ev);
+            if (q == cudaSuccess) return;
+            if (q != cudaErrorNotReady) throw_cuda(q, "cudaEventQuery(sync)", __FILE__, __LINE__);
+        }
+    }
+    CWCU_CHECK(cudaEventSynchronize(ev)); // blocks (cudaEventBlockingSync): the thread sleeps until the GPU interrupt
 }
 
 bool is_pinned_host(const void *p) {

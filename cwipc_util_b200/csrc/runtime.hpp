@@ -86,6 +86,12 @@ struct Scratch {
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
+// Wait until everything queued on `s` so far has completed.  Polls for $CWIPC_CUDA_SPIN_US (default 20) microseconds
+// -- the usual wait is a count readback behind one or two short kernels -- then naps $CWIPC_CUDA_SLEEP_US (default 20)
+// between polls, so that many caller threads can share few cores (measured: 15 threads on 4 cores lose nothing against
+// 10 polling threads on 16).  CWIPC_CUDA_SLEEP_US=0 blocks in the driver instead (interrupt wake-up, slow in VMs).
+void stream_sync(cudaStream_t s);
+
 // ---- events ----
 cudaEvent_t event_acquire();             // timing disabled
 void event_release(cudaEvent_t e) noexcept;
