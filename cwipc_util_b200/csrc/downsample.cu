@@ -391,7 +391,7 @@ static_assert(sizeof(VoxelSlot) == 64, "one slot per 64 bytes");
 struct TableHeader { // first 64 bytes of the zeroed workspace
     uint32_t count; // claimed slots
     uint32_t error; // out-of-range coordinate seen
-    uint32_t pad[14]; // pad[0]: last-block ticket of bbox_octree_kernel; pad[2..3]: barrier words of radix_fused_kernel
+    uint32_t pad[14]; // pad[0]: last-block ticket of bbox_octree_kernel; pad[2..3]: barrier words of radix_fused_kernel; pad[4]: stats ticket
 };
 
 __device__ __forceinline__ uint32_t hash_key(uint64_t k) {

@@ -15,6 +15,7 @@ struct Predicate {
     float box[6] = {0, 0, 0, 0, 0, 0}; // CropBox: minx,maxx,miny,maxy,minz,maxz
     const float *dist = nullptr;  // DistanceAtMost: keep iff !(dist[i] > threshold)
     double threshold = 0.0;
+    const double *threshold_dev = nullptr; // when not null the threshold is read from device memory instead
 };
 
 // Stable compaction of in[0..n) by `pred` into out (capacity >= n).  Returns the number kept.

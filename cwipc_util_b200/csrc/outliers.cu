@@ -652,6 +652,51 @@ __global__ void __launch_bounds__(ST_THREADS) stats_kernel(const float *__restri
     }
 }
 
+// Same reduction, and the block that finishes last adds the 256 partials in index order and derives the threshold
+// (mean + mul * unbiased stddev, all in double as pcl::StatisticalOutlierRemoval) on the device, so that the keep
+// mask can be taken without a host round trip.
+__global__ void __launch_bounds__(ST_THREADS) stats_threshold_kernel(const float *__restrict__ dist, uint32_t n, double *partial, uint32_t *__restrict__ done_counter,
+                                                                      double stddev_mul, double *__restrict__ threshold_out) {
+    __shared__ double s_sum[ST_THREADS], s_sq[ST_THREADS];
+    __shared__ bool s_last;
+    double sum = 0.0, sq = 0.0;
+    for (uint32_t i = blockIdx.x * ST_THREADS + threadIdx.x; i < n; i += ST_BLOCKS * ST_THREADS) {
+        const float d = dist[i];
+        sum += (double)d;
+        sq += (double)__fmul_rn(d, d);
+    }
+    s_sum[threadIdx.x] = sum;
+    s_sq[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = ST_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+            s_sq[threadIdx.x] += s_sq[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __stcg(partial + 2 * blockIdx.x, s_sum[0]);
+        __stcg(partial + 2 * blockIdx.x + 1, s_sq[0]);
+        __threadfence();
+        const uint32_t ticket = atomicAdd(done_counter, 1u);
+        s_last = ticket == ST_BLOCKS - 1;
+        if (s_last) *done_counter = 0; // clean for the next call
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    double tsum = 0.0, tsq = 0.0;
+    for (int b = 0; b < ST_BLOCKS; b++) {
+        tsum += __ldcg(partial + 2 * b);
+        tsq += __ldcg(partial + 2 * b + 1);
+    }
+    const double dn = (double)n;
+    const double mean = tsum / dn;
+    const double variance = (tsq - tsum * tsum / dn) / (dn - 1.0);
+    *threshold_out = mean + stddev_mul * sqrt(variance);
+}
+
 int bit_length(uint64_t v) {
     int b = 0;
     while (v) {
@@ -882,12 +927,17 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
     }
     Scratch dist(n * sizeof(float), s);
     knn_mean_distances(in, n, k, hint_spacing, bounds, dist.as<float>(), dev, s);
-    double sums[2];
-    distance_stats(dist.as<float>(), n, sums, s);
+    // statistics and threshold stay on the device: the compaction reads the threshold from memory
+    Scratch partial((2 * ST_BLOCKS + 1) * sizeof(double), s);
+    uint32_t *counter = static_cast<uint32_t *>(thread_zeroed(dev, 64, s)) + 6; // word 6 of the zeroed workspace header
+    double *d_thr = partial.as<double>() + 2 * ST_BLOCKS;
+    launch("stats_kernel", s, 4 * (size_t)n, [&] {
+        stats_threshold_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>(), counter, (double)stddev_mul, d_thr);
+    });
     Predicate p;
     p.kind = PredKind::DistanceAtMost;
     p.dist = dist.as<float>();
-    p.threshold = outlier_threshold(sums[0], sums[1], (double)n, stddev_mul);
+    p.threshold_dev = d_thr;
     return compact_points(in, n, out, p, dev, s);
 }
 

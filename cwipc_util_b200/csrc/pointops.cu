@@ -40,6 +40,11 @@ struct DistPred {
     // keep iff !(d > thr), float promoted to double as in PCL's second pass
     __device__ __forceinline__ bool operator()(const Point16 &, uint32_t i) const { return !((double)dist[i] > threshold); }
 };
+struct DistPredDev { // threshold produced on the device by stats_threshold_kernel
+    const float *dist;
+    const double *threshold;
+    __device__ __forceinline__ bool operator()(const Point16 &, uint32_t i) const { return !((double)dist[i] > __ldg(threshold)); }
+};
 
 template <class Pred>
 __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *__restrict__ in, uint32_t n, cwipc_point *__restrict__ out, Pred pred,
@@ -196,6 +201,7 @@ size_t compact_points(const cwipc_point *in, size_t n, cwipc_point *out, const P
     case PredKind::CropBox:
         return run_compact(in, n, out, CropPred{pred.box[0], pred.box[1], pred.box[2], pred.box[3], pred.box[4], pred.box[5]}, s);
     case PredKind::DistanceAtMost:
+        if (pred.threshold_dev) return run_compact(in, n, out, DistPredDev{pred.dist, pred.threshold_dev}, s, 20);
         return run_compact(in, n, out, DistPred{pred.dist, pred.threshold}, s, 20);
     }
     return 0;

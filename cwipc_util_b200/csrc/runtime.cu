@@ -27,6 +27,7 @@ struct DeviceState {
     std::mutex mu;
     std::vector<cudaStream_t> idle_streams; // streams returned by exited threads
     std::vector<std::pair<void *, size_t>> idle_zeroed; // workspaces returned by exited threads (contents unknown)
+    std::vector<std::pair<char *, size_t>> idle_arena;  // scratch arena blocks returned by exited threads
 };
 
 int g_ndev = -1;
@@ -71,6 +72,13 @@ struct ThreadState {
     void *pinned = nullptr;
     size_t pinned_size = 0;
     cudaEvent_t sync_event[64] = {nullptr}; // per device, created with cudaEventBlockingSync
+    struct Arena {
+        std::vector<std::pair<char *, size_t>> blocks; // the last one is the current one
+        size_t offset = 0;  // in the current block
+        size_t used = 0;    // bytes handed out since the last rewind (all blocks)
+        int live = 0;       // Scratch objects alive
+    };
+    std::vector<Arena> arenas; // per device
     struct Zeroed {
         void *p = nullptr;
         size_t size = 0;
@@ -93,6 +101,12 @@ struct ThreadState {
                     std::lock_guard<std::mutex> lk(g_devs[d].mu);
                     g_devs[d].idle_zeroed.emplace_back(zeroed[d].p, zeroed[d].size);
                 }
+            }
+        }
+        if (g_devs) {
+            for (size_t d = 0; d < arenas.size(); d++) {
+                std::lock_guard<std::mutex> lk(g_devs[d].mu);
+                for (auto &b : arenas[d].blocks) g_devs[d].idle_arena.push_back(b);
             }
         }
         // the pinned scratch is deliberately not freed: the CUDA runtime may already be gone
@@ -169,6 +183,70 @@ void dfree(void *p, cudaStream_t s) noexcept {
     if (!p) return;
     cudaError_t e = cudaFreeAsync(p, s);
     if (e != cudaSuccess) (void)cudaGetLastError();
+}
+
+void *scratch_alloc(size_t bytes, cudaStream_t s, bool *from_arena) {
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    *from_arena = false;
+    if ((int)t_state.streams.size() <= dev || t_state.streams[dev] != s) return dmalloc(bytes, s); // not this thread's stream
+    if ((int)t_state.arenas.size() <= dev) t_state.arenas.resize(dev + 1);
+    auto &a = t_state.arenas[dev];
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (a.blocks.empty()) { // adopt a block an exited thread left behind, if it is large enough
+        DeviceState &st = g_devs[dev];
+        bool adopted = false;
+        {
+            std::lock_guard<std::mutex> lk(st.mu);
+            for (size_t i = 0; i < st.idle_arena.size(); i++) {
+                if (st.idle_arena[i].second >= need) {
+                    a.blocks.push_back(st.idle_arena[i]);
+                    st.idle_arena.erase(st.idle_arena.begin() + (long)i);
+                    adopted = true;
+                    break;
+                }
+            }
+        }
+        if (adopted) CWCU_CHECK(cudaDeviceSynchronize()); // its previous owner's stream may still be draining (rare: thread start-up)
+        a.offset = 0;
+    }
+    if (a.blocks.empty() || a.offset + need > a.blocks.back().second) {
+        size_t cap = a.blocks.empty() ? ((size_t)8 << 20) : a.blocks.back().second * 2;
+        while (cap < need) cap *= 2;
+        a.blocks.emplace_back(static_cast<char *>(dmalloc(cap, s)), cap);
+        a.offset = 0;
+    }
+    char *p = a.blocks.back().first + a.offset;
+    a.offset += need;
+    a.used += need;
+    a.live++;
+    *from_arena = true;
+    return p;
+}
+
+void scratch_free(void *p, cudaStream_t s, bool from_arena) noexcept {
+    if (!from_arena) {
+        dfree(p, s);
+        return;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if ((int)t_state.arenas.size() <= dev) return;
+    auto &a = t_state.arenas[dev];
+    if (--a.live > 0) return;
+    // rewind; if the call needed more than one block, replace them by one that holds everything
+    if (a.blocks.size() > 1) {
+        size_t cap = a.blocks.back().second;
+        while (cap < a.used) cap *= 2;
+        for (auto &b : a.blocks) dfree(b.first, s);
+        a.blocks.clear();
+        void *q = nullptr;
+        if (cudaMallocAsync(&q, cap, s) == cudaSuccess) a.blocks.emplace_back(static_cast<char *>(q), cap);
+        else (void)cudaGetLastError();
+    }
+    a.offset = 0;
+    a.used = 0;
+    a.live = 0;
 }
 
 void *thread_pinned(size_t bytes) {

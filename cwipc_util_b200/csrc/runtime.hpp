@@ -68,21 +68,29 @@ bool is_pinned_host(const void *p);
 void *thread_zeroed(int dev, size_t bytes, cudaStream_t s);
 void thread_zeroed_invalidate(int dev);
 
-// Scratch block freed (stream-ordered) at scope exit.
+// Scratch block, released at scope exit.  Scratch comes from a per-thread, per-device arena (one cudaMallocAsync'd
+// block, bump allocation) when it is requested on the thread's own stream: kernels of successive calls of one thread
+// are ordered on that stream, so the bytes can be reused without any driver call.  The arena rewinds when the last
+// live Scratch of the thread is released (i.e. at the end of every filter call); a call that outgrows it chains a
+// larger block, and the blocks are merged at the next rewind.  Other streams fall back to cudaMallocAsync.
+void *scratch_alloc(size_t bytes, cudaStream_t s, bool *from_arena);
+void scratch_free(void *p, cudaStream_t s, bool from_arena) noexcept;
+
 struct Scratch {
     void *p = nullptr;
     cudaStream_t s = nullptr;
+    bool arena = false;
     Scratch() = default;
-    Scratch(size_t bytes, cudaStream_t stream) : p(bytes ? dmalloc(bytes, stream) : nullptr), s(stream) {}
+    Scratch(size_t bytes, cudaStream_t stream) : s(stream) { p = bytes ? scratch_alloc(bytes, stream, &arena) : nullptr; }
     Scratch(const Scratch &) = delete;
     Scratch &operator=(const Scratch &) = delete;
-    Scratch(Scratch &&o) noexcept : p(o.p), s(o.s) { o.p = nullptr; }
+    Scratch(Scratch &&o) noexcept : p(o.p), s(o.s), arena(o.arena) { o.p = nullptr; }
     Scratch &operator=(Scratch &&o) noexcept {
-        if (this != &o) { release(); p = o.p; s = o.s; o.p = nullptr; }
+        if (this != &o) { release(); p = o.p; s = o.s; arena = o.arena; o.p = nullptr; }
         return *this;
     }
     ~Scratch() { release(); }
-    void release() noexcept { if (p) { dfree(p, s); p = nullptr; } }
+    void release() noexcept { if (p) { scratch_free(p, s, arena); p = nullptr; } }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
