@@ -684,12 +684,17 @@ __global__ void __launch_bounds__(ST_THREADS) stats_threshold_kernel(const float
         if (s_last) *done_counter = 0; // clean for the next call
     }
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if (!s_last) return;
     __threadfence();
+    static_assert(ST_BLOCKS == ST_THREADS, "one partial per thread");
+    s_sum[threadIdx.x] = __ldcg(partial + 2 * threadIdx.x); // parallel fetch, then one thread adds in index order
+    s_sq[threadIdx.x] = __ldcg(partial + 2 * threadIdx.x + 1);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double tsum = 0.0, tsq = 0.0;
     for (int b = 0; b < ST_BLOCKS; b++) {
-        tsum += __ldcg(partial + 2 * b);
-        tsq += __ldcg(partial + 2 * b + 1);
+        tsum += s_sum[b];
+        tsq += s_sq[b];
     }
     const double dn = (double)n;
     const double mean = tsum / dn;

@@ -546,12 +546,20 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
     if (npasses > RS_MAX_PASSES) throw CudaError{cudaErrorInvalidValue, "radix_sort_u64: bit range too wide"};
     const size_t ntiles = div_up(n, RS_TILE);
 
-    // one cluster of <= 8 CTAs sorts up to 8 x 512 x 24 words entirely in distributed shared memory
-    if (n <= (size_t)RC_MAX_CTAS * RC_THREADS * 8) {
-        if (launch_cluster_sort<8>(a, b, n, begin_bit, end_bit, dev, s)) return b;
-    } else if (n <= (size_t)RC_MAX_CTAS * RC_THREADS * 24) {
-        if (launch_cluster_sort<24>(a, b, n, begin_bit, end_bit, dev, s)) return b;
-    }
+    // one cluster of <= 8 CTAs sorts up to 8 x 512 x 24 words entirely in distributed shared memory.  A pass is bound
+    // by the shared-memory pipe of each SM (match/LDS/STS per key), so the keys are spread over all 8 CTAs: the
+    // smallest per-thread count that fits
+    const size_t per_ipt = (size_t)RC_MAX_CTAS * RC_THREADS;
+    bool done = false, tried = true;
+    if (n <= per_ipt * 2) done = launch_cluster_sort<2>(a, b, n, begin_bit, end_bit, dev, s);
+    else if (n <= per_ipt * 4) done = launch_cluster_sort<4>(a, b, n, begin_bit, end_bit, dev, s);
+    else if (n <= per_ipt * 8) done = launch_cluster_sort<8>(a, b, n, begin_bit, end_bit, dev, s);
+    else if (n <= per_ipt * 12) done = launch_cluster_sort<12>(a, b, n, begin_bit, end_bit, dev, s);
+    else if (n <= per_ipt * 16) done = launch_cluster_sort<16>(a, b, n, begin_bit, end_bit, dev, s);
+    else if (n <= per_ipt * 24) done = launch_cluster_sort<24>(a, b, n, begin_bit, end_bit, dev, s);
+    else tried = false;
+    (void)tried;
+    if (done) return b;
     if ((int)ntiles <= fused_tile_limit(dev)) {
         const int fpasses = fused_passes(end_bit - begin_bit);
         Scratch hist(2 * ntiles * RF_BINS * sizeof(uint32_t), s);
