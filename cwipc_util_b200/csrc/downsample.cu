@@ -388,7 +388,7 @@ struct __align__(64) VoxelSlot {
 };
 static_assert(sizeof(VoxelSlot) == 64, "one slot per 64 bytes");
 
-struct TableHeader { // first 64 bytes of the zeroed workspace
+struct TableHeader { // first 64 bytes of the zeroed workspace (layout of the whole head: runtime.hpp, ZW_HEADER_BYTES)
     uint32_t count; // claimed slots
     uint32_t error; // out-of-range coordinate seen
     uint32_t pad[14]; // pad[0]: last-block ticket of bbox_octree_kernel; pad[2..3]: barrier words of radix_fused_kernel; pad[4]: stats ticket
@@ -545,7 +545,7 @@ int bit_length(uint64_t v) {
 
 // the "last block" ticket of bbox_octree_kernel: a word of the thread's zeroed workspace header (pad[0])
 uint32_t *bbox_counter(int dev, cudaStream_t s) {
-    TableHeader *h = static_cast<TableHeader *>(thread_zeroed(dev, sizeof(TableHeader), s));
+    TableHeader *h = static_cast<TableHeader *>(thread_zeroed(dev, ZW_HEADER_BYTES, s));
     return &h->pad[0];
 }
 
@@ -739,9 +739,9 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
     // hash table in the thread's zeroed workspace: [header | capacity slots], load factor <= 2/3
     const size_t capacity = plan.capacity;
     const int slotbits = plan.slotbits;
-    uint8_t *ws = static_cast<uint8_t *>(thread_zeroed(dev, sizeof(TableHeader) + capacity * sizeof(VoxelSlot), s));
+    uint8_t *ws = static_cast<uint8_t *>(thread_zeroed(dev, ZW_HEADER_BYTES + capacity * sizeof(VoxelSlot), s));
     TableHeader *header = reinterpret_cast<TableHeader *>(ws);
-    VoxelSlot *table = reinterpret_cast<VoxelSlot *>(ws + sizeof(TableHeader));
+    VoxelSlot *table = reinterpret_cast<VoxelSlot *>(ws + ZW_HEADER_BYTES);
     try {
         Scratch list(n * sizeof(uint64_t), s);
         launch("voxel_accumulate_kernel", s, 16 * (size_t)n, [&] {

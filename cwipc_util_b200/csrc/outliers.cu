@@ -87,7 +87,11 @@ __device__ __forceinline__ float dist2(const Point16 &a, const Point16 &b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__global__ void __launch_bounds__(256) knn_keygen_kernel(const cwipc_point *__restrict__ pts, uint32_t n, GridParams gp, uint64_t *__restrict__ keys) {
+__global__ void __launch_bounds__(256) knn_keygen_kernel(const cwipc_point *__restrict__ pts, uint32_t n, GridParams gp, uint64_t *__restrict__ keys, uint2 *__restrict__ table,
+                                                          uint32_t table_words2) {
+    // the table pyramid (and the far-query counter behind it) must start empty: cleared here, two launches before
+    // knn_layout_kernel fills it, instead of by a separate memset
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < table_words2; i += gridDim.x * blockDim.x) table[i] = make_uint2(0u, 0u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Point16 p = ld_point_stream(pts, i);
         const uint32_t cx = cell_of(cell_u(p.x, gp.gmin[0], gp.inv_h), gp.gdim[0]);
@@ -830,14 +834,16 @@ void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hin
 
     ix.keys_a = Scratch(n * sizeof(uint64_t), s);
     ix.keys_b = Scratch(n * sizeof(uint64_t), s);
-    launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] { knn_keygen_kernel<<<stream_grid(n, dev), 256, 0, s>>>(in, (uint32_t)n, gp, ix.keys_a.as<uint64_t>()); });
+    // cell-ordered points, table pyramid, far-query counter (2 extra entries behind the tables)
+    ix.spts = Scratch(n * sizeof(cwipc_point), s);
+    ix.table = Scratch((plan.table_entries + 2) * sizeof(uint2), s);
+    ix.far_count = reinterpret_cast<uint32_t *>(ix.table.as<uint2>() + plan.table_entries);
+    launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] {
+        knn_keygen_kernel<<<stream_grid(std::max(n, plan.table_entries / 4), dev), 256, 0, s>>>(in, (uint32_t)n, gp, ix.keys_a.as<uint64_t>(), ix.table.as<uint2>(),
+                                                                                                 (uint32_t)(plan.table_entries + 2));
+    });
     ix.sorted = radix_sort_u64(ix.keys_a.as<uint64_t>(), ix.keys_b.as<uint64_t>(), n, gp.idxbits, gp.idxbits + keybits, dev, s);
 
-    // cell-ordered points, table pyramid, far-query counter
-    ix.spts = Scratch(n * sizeof(cwipc_point), s);
-    ix.table = Scratch(plan.table_entries * sizeof(uint2) + 16, s);
-    CWCU_CHECK(cudaMemsetAsync(ix.table.p, 0, plan.table_entries * sizeof(uint2) + 16, s));
-    ix.far_count = reinterpret_cast<uint32_t *>(ix.table.as<uint2>() + plan.table_entries);
     launch("knn_layout_kernel", s, 48 * (size_t)n, [&] {
         knn_layout_kernel<<<stream_grid(n, dev), 256, 0, s>>>(ix.sorted, (uint32_t)n, gp, in, ix.spts.as<cwipc_point>(), ix.table.as<uint2>());
     });
@@ -934,7 +940,7 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
     knn_mean_distances(in, n, k, hint_spacing, bounds, dist.as<float>(), dev, s);
     // statistics and threshold stay on the device: the compaction reads the threshold from memory
     Scratch partial((2 * ST_BLOCKS + 1) * sizeof(double), s);
-    uint32_t *counter = static_cast<uint32_t *>(thread_zeroed(dev, 64, s)) + 6; // word 6 of the zeroed workspace header
+    uint32_t *counter = static_cast<uint32_t *>(thread_zeroed(dev, ZW_HEADER_BYTES, s)) + 6; // word 6 of the zeroed workspace header
     double *d_thr = partial.as<double>() + 2 * ST_BLOCKS;
     launch("stats_kernel", s, 4 * (size_t)n, [&] {
         stats_threshold_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>(), counter, (double)stddev_mul, d_thr);

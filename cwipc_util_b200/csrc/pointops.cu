@@ -48,7 +48,7 @@ struct DistPredDev { // threshold produced on the device by stats_threshold_kern
 
 template <class Pred>
 __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *__restrict__ in, uint32_t n, cwipc_point *__restrict__ out, Pred pred,
-                                                              uint32_t *__restrict__ ticket, uint64_t *__restrict__ status, uint32_t *__restrict__ d_total) {
+                                                              uint32_t *__restrict__ ticket, uint64_t *status, uint32_t *__restrict__ d_total, uint32_t *done_counter) {
     __shared__ int s_tile;
     __shared__ uint32_t s_warp_total[CP_THREADS / 32];
     __shared__ uint32_t s_tile_excl;
@@ -103,21 +103,51 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *
     for (int i = 0; i < CP_ITEMS; i++) {
         if (keepbits & (1u << i)) st_point(out, base + rank[i], pts[i]);
     }
+    // The look-back words live in the thread's zeroed workspace: the block that finishes last (nobody reads them any
+    // more) clears them and the counters, so the next launch finds zeros without a memset.
+    if (done_counter) {
+        __shared__ bool s_last_done;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last_done = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last_done) {
+            for (uint32_t t = threadIdx.x; t < gridDim.x; t += CP_THREADS) status[t] = 0;
+            if (threadIdx.x == 0) {
+                *ticket = 0;
+                *done_counter = 0;
+            }
+        }
+    }
 }
 
 template <class Pred>
 size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred, cudaStream_t s, size_t pred_bytes = 16) {
     if (n == 0) return 0;
     const size_t ntiles = div_up(n, CP_TILE);
-    // [ticket u32 | total u32 | status u64 * ntiles]
-    const size_t bytes = 8 + ntiles * sizeof(uint64_t);
-    Scratch scratch(bytes, s);
-    CWCU_CHECK(cudaMemsetAsync(scratch.p, 0, bytes, s));
-    uint32_t *ticket = scratch.as<uint32_t>();
-    uint32_t *d_total = ticket + 1;
-    uint64_t *status = reinterpret_cast<uint64_t *>(ticket + 2);
+    // [ticket u32 | total u32 | done u32 | pad | status u64 * ntiles]: in the zeroed workspace (cleared by the kernel itself)
+    // when it fits, else in scratch that is memset first
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    Scratch scratch;
+    uint32_t *words;
+    uint32_t *done = nullptr;
+    if (ntiles <= ZW_COMPACT_TILES && thread_stream(dev) == s) {
+        words = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(thread_zeroed(dev, ZW_HEADER_BYTES, s)) + ZW_COMPACT_OFFSET);
+        done = words + 2;
+    } else {
+        const size_t bytes = 16 + ntiles * sizeof(uint64_t);
+        scratch = Scratch(bytes, s);
+        CWCU_CHECK(cudaMemsetAsync(scratch.p, 0, bytes, s));
+        words = scratch.as<uint32_t>();
+    }
+    uint32_t *ticket = words;
+    uint32_t *d_total = words + 1;
+    uint64_t *status = reinterpret_cast<uint64_t *>(words + 4);
     launch("compact_kernel", s, pred_bytes * (size_t)n, [&] {
-        compact_kernel<Pred><<<(unsigned)ntiles, CP_THREADS, 0, s>>>(in, (uint32_t)n, out, pred, ticket, status, d_total);
+        compact_kernel<Pred><<<(unsigned)ntiles, CP_THREADS, 0, s>>>(in, (uint32_t)n, out, pred, ticket, status, d_total, done);
     });
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -565,7 +565,7 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
         Scratch hist(2 * ntiles * RF_BINS * sizeof(uint32_t), s);
         uint32_t *tile_hist = hist.as<uint32_t>();
         uint32_t n32 = (uint32_t)n;
-        uint32_t *sync_words = static_cast<uint32_t *>(thread_zeroed(dev, 64, s)) + 4; // words 4,5 of the zeroed workspace header
+        uint32_t *sync_words = static_cast<uint32_t *>(thread_zeroed(dev, ZW_HEADER_BYTES, s)) + 4; // words 4,5 of the zeroed workspace header
         void *args[] = {&a, &b, &n32, &begin_bit, &end_bit, &tile_hist, &sync_words};
         launch("radix_fused_kernel", s, 16 * (size_t)n * fpasses, [&] {
             CWCU_CHECK(cudaLaunchCooperativeKernel((const void *)radix_fused_kernel, dim3((unsigned)ntiles), dim3(RS_THREADS), args, RF_SMEM_BYTES, s));

@@ -66,6 +66,16 @@ bool is_pinned_host(const void *p);
 // entry clears it), so that steady-state calls need no memset.  Work on it must be queued on `s`,
 // the thread's stream.  Call thread_zeroed_invalidate() when a failure may have left it dirty.
 void *thread_zeroed(int dev, size_t bytes, cudaStream_t s);
+// Head of that workspace, shared by the kernels that need a few zero-initialised words per launch and clear them
+// again before they exit (so that no launch needs a memset):
+//   words 0,1    voxel table: claimed-slot count, error flag                    (downsample.cu)
+//   word  2      bbox_octree_kernel: last-block ticket
+//   words 4,5    radix_fused_kernel: grid barrier
+//   word  6      stats_threshold_kernel: last-block ticket
+//   bytes 256..  compact_kernel: ticket, total, done, pad, then one 64-bit look-back word per 2048-point tile
+constexpr size_t ZW_HEADER_BYTES = 65536;
+constexpr size_t ZW_COMPACT_OFFSET = 256;
+constexpr size_t ZW_COMPACT_TILES = (ZW_HEADER_BYTES - ZW_COMPACT_OFFSET - 16) / 8;
 void thread_zeroed_invalidate(int dev);
 
 // Scratch block, released at scope exit.  Scratch comes from a per-thread, per-device arena (one cudaMallocAsync'd
