@@ -312,6 +312,17 @@ void stream_sync(cudaStream_t s) {
         const char *e = getenv("CWIPC_CUDA_SLEEP_US");
         return (e && *e) ? atol(e) * 1000L : 20000L;
     }();
+    static const bool spin_given = [] { const char *e = getenv("CWIPC_CUDA_SPIN_US"); return e && *e; }();
+    static std::atomic<int> waiters{0};
+    struct WaiterScope {
+        std::atomic<int> &c;
+        int mine;
+        explicit WaiterScope(std::atomic<int> &c_) : c(c_), mine(c_.fetch_add(1) + 1) {}
+        ~WaiterScope() { c.fetch_sub(1); }
+    } scope(waiters);
+    // one or two callers: polling costs nothing and saves the ~60 us a nap overshoots by (single-call latency);
+    // many callers: short polling budget, then naps
+    const long budget_ns = (!spin_given && scope.mine <= 2) ? 500000L : spin_ns;
     int dev = 0;
     CWCU_CHECK(cudaGetDevice(&dev));
     cudaEvent_t &ev = t_state.sync_event[dev & 63];
@@ -325,7 +336,7 @@ void stream_sync(cudaStream_t s) {
         if (q != cudaErrorNotReady) throw_cuda(q, "cudaEventQuery(sync)", __FILE__, __LINE__);
         timespec t1;
         clock_gettime(CLOCK_MONOTONIC, &t1);
-        if ((t1.tv_sec - t0.tv_sec) * 1000000000L + (t1.tv_nsec - t0.tv_nsec) >= spin_ns) break;
+        if ((t1.tv_sec - t0.tv_sec) * 1000000000L + (t1.tv_nsec - t0.tv_nsec) >= budget_ns) break;
     }
     if (sleep_ns > 0) {
         // few cores, many waiting threads: give the core away between polls (a blocking wait in the driver wakes up
