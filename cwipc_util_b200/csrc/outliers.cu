@@ -19,7 +19,7 @@
 //                       threshold + bitonic merge keeps the k+1 smallest distances in sorted registers.
 //                       A query is final when its (k+1)-th distance is within Rc pitches; the rest is queued.
 //   knn_far_kernel      one warp per queued query: depth-first search of the table pyramid (an implicit
-//                       octree), nearest child first, pruned by the running (k+1)-th best.
+//                       octree), four nearest open nodes per step, pruned by the running (k+1)-th best.
 //   stats_kernel        sum d, sum (float)(d*d) in double, fixed two-level order (deterministic)
 //   compact_kernel      keep mask + stable compaction (pointops.cu)
 // Exactness never depends on the grid pitch; the pitch only moves work between the two passes.
@@ -418,14 +418,13 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
 // through warp-shuffle bitonic networks.
 constexpr int KF_WARPS = 4;
 constexpr int KF_THREADS = KF_WARPS * 32;
-constexpr int KF_STACK = 112; // >= 7 * top_level + 8 with top_level <= 13
+constexpr int KF_STACK = 416; // four nodes are expanded per step: <= 28 * top_level + 32 open nodes with top_level <= 13
 
-struct FarNode { // 32 B
+struct FarNode { // 20 B
     uint32_t pb, pe;  // point range
-    uint32_t x, y, z; // node coordinates at its level
-    int level;
+    uint32_t xy;      // node coordinates at its level: x | y << 16
+    uint32_t zl;      // z | level << 16
     float mind2;
-    uint32_t pad;
 };
 
 __device__ __forceinline__ float warp_bitonic_sort32(float x, unsigned lane) { // ascending along the lanes
@@ -452,6 +451,38 @@ __device__ __forceinline__ float warp_bitonic_merge32(float x, unsigned lane) { 
 
 // The kk nearest squared distances from q to the cloud, ascending along (lane, register): element e
 // lives in lane e % 32, register e / 32.  Called by all 32 lanes of a warp with the same arguments.
+// One batch of up to 32 candidate distances into the lane-distributed sorted list (element e in lane e % 32,
+// register e / 32); returns the new kk-th smallest.
+template <int KPL>
+__device__ __forceinline__ float list_absorb(float (&v)[KPL], float d2, bool pass, unsigned pm, int kk, unsigned lane) {
+    if (KPL == 1 && __popc(pm) <= 6) {
+        // few survivors: insert them one by one
+        while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const float x = __shfl_sync(FULL_MASK, d2, src);
+            const float up = __shfl_up_sync(FULL_MASK, v[0], 1);
+            if (v[0] > x) v[0] = (lane == 0) ? x : fmaxf(up, x);
+        }
+    } else {
+        const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
+        const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
+        if (KPL == 1) {
+            v[0] = warp_bitonic_merge32(fminf(v[0], r), lane);
+        } else {
+            v[KPL - 1] = fminf(v[KPL - 1], r);
+            const float lo = fminf(v[0], v[KPL - 1]), hi = fmaxf(v[0], v[KPL - 1]);
+            v[0] = warp_bitonic_merge32(lo, lane);
+            v[KPL - 1] = warp_bitonic_merge32(hi, lane);
+        }
+    }
+    return __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
+}
+
+// The kk nearest squared distances from q to the cloud, ascending along (lane, register): element e
+// lives in lane e % 32, register e / 32.  Called by all 32 lanes of a warp with the same arguments.
+// Every iteration takes the (up to) four nearest open nodes off the stack: the small ones are scanned, the
+// others are expanded together, eight lanes per node, one child per lane.
 template <int KPL>
 __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Point16 *__restrict__ spts16, uint32_t n, const GridParams &gp, int kk,
                                         const uint2 *__restrict__ table, uint32_t leaf_points, FarNode *stack, float (&v)[KPL]) {
@@ -463,86 +494,88 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
 
     if (lane == 0) {
         FarNode root;
-        root.pb = 0; root.pe = n; root.x = root.y = root.z = 0; root.level = gp.top_level; root.mind2 = 0.f; root.pad = 0;
+        root.pb = 0; root.pe = n; root.xy = 0; root.zl = (uint32_t)gp.top_level << 16; root.mind2 = 0.f;
         stack[0] = root;
     }
     int sp = 1;
     __syncwarp();
+    const int group = (int)(lane >> 3);
     while (sp > 0) {
-        const FarNode node = stack[--sp];
+        const int take = min(sp, 4);
+        // lane group g looks at the g-th node from the top (g = 0 is the nearest)
+        const FarNode node = stack[sp - 1 - min(group, take - 1)];
+        const bool have = group < take;
+        const uint32_t node_x = node.xy & 0xffffu, node_y = node.xy >> 16, node_z = node.zl & 0xffffu;
+        const int node_level = (int)(node.zl >> 16);
+        sp -= take;
         __syncwarp();
-        const float thr = fminf(tau, limit);
-        if (node.mind2 * 0.9999f > thr) continue;
-        if (node.level == 0 || node.pe - node.pb <= leaf_points) {
-            for (uint32_t base = node.pb; base < node.pe; base += 32) {
+        // small nodes first (nearest first): scanning them tightens the bound for the expansions below
+        for (int j = 0; j < take; j++) {
+            const uint32_t pb = __shfl_sync(FULL_MASK, node.pb, j * 8), pe = __shfl_sync(FULL_MASK, node.pe, j * 8);
+            const int level = __shfl_sync(FULL_MASK, node_level, j * 8);
+            const float nm = __shfl_sync(FULL_MASK, node.mind2, j * 8);
+            if (!(level == 0 || pe - pb <= leaf_points)) continue;
+            if (nm * 0.9999f > fminf(tau, limit)) continue;
+            for (uint32_t base = pb; base < pe; base += 32) {
                 const uint32_t c = base + lane;
                 float d2 = INFINITY;
-                if (c < node.pe) d2 = dist2(q, spts16[c]);
+                if (c < pe) d2 = dist2(q, spts16[c]);
                 const bool pass = d2 < tau && d2 <= limit;
-                unsigned pm = __ballot_sync(FULL_MASK, pass);
-                if (pm == 0u) continue;
-                if (KPL == 1 && __popc(pm) <= 6) {
-                    // few survivors: insert them one by one into the lane-distributed sorted list
-                    while (pm) {
-                        const int src = __ffs(pm) - 1;
-                        pm &= pm - 1;
-                        const float x = __shfl_sync(FULL_MASK, d2, src);
-                        const float up = __shfl_up_sync(FULL_MASK, v[0], 1);
-                        if (v[0] > x) v[0] = (lane == 0) ? x : fmaxf(up, x);
-                    }
-                    tau = __shfl_sync(FULL_MASK, v[0], (kk - 1) & 31);
-                    continue;
-                }
-                const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
-                const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
-                if (KPL == 1) {
-                    v[0] = warp_bitonic_merge32(fminf(v[0], r), lane);
-                } else {
-                    v[KPL - 1] = fminf(v[KPL - 1], r);
-                    const float lo = fminf(v[0], v[KPL - 1]), hi = fmaxf(v[0], v[KPL - 1]);
-                    v[0] = warp_bitonic_merge32(lo, lane);
-                    v[KPL - 1] = warp_bitonic_merge32(hi, lane);
-                }
-                tau = __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
+                const unsigned pm = __ballot_sync(FULL_MASK, pass);
+                if (pm) tau = list_absorb<KPL>(v, d2, pass, pm, kk, lane);
             }
-        } else {
-            // children at level-1: lanes 0..7 look one child up each
-            const int cl = node.level - 1;
-            const uint32_t chx = 2u * node.x + ((lane >> 2) & 1u), chy = 2u * node.y + ((lane >> 1) & 1u), chz = 2u * node.z + (lane & 1u);
-            uint2 r = make_uint2(0u, 0u);
-            float mind2 = INFINITY;
-            bool admit = false;
-            if (lane < 8 && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl)) {
-                r = table[table_index(gp, cl, chx, chy, chz)];
-                if (r.y > r.x) {
-                    const float pitch = ldexpf(gp.h, cl);
-                    const float lo[3] = {gp.gmin[0] + (float)chx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
-                    const float qq[3] = {q.x, q.y, q.z};
-                    mind2 = 0.f;
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
-                        mind2 += d * d;
-                    }
-                    admit = mind2 * 0.9999f <= thr;
-                }
-            }
-            const unsigned adm = __ballot_sync(FULL_MASK, admit);
-            const int nadm = __popc(adm);
-            int rank = 0; // position among the admitted children, nearest first
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float mj = __shfl_sync(FULL_MASK, mind2, j);
-                if (((adm >> j) & 1u) && (mj < mind2 || (mj == mind2 && j < (int)lane))) rank++;
-            }
-            if (admit) {
-                FarNode ch;
-                ch.pb = r.x; ch.pe = r.y; ch.x = chx; ch.y = chy; ch.z = chz; ch.level = cl; ch.mind2 = mind2; ch.pad = 0;
-                stack[sp + nadm - 1 - rank] = ch; // farthest deepest, nearest on top
-            }
-            sp += nadm;
-            __syncwarp();
         }
+        // the others: one child per lane
+        const float thr = fminf(tau, limit);
+        const bool expand = have && !(node_level == 0 || node.pe - node.pb <= leaf_points) && !(node.mind2 * 0.9999f > thr);
+        const int cl = node_level - 1;
+        const uint32_t chx = 2u * node_x + ((lane >> 2) & 1u), chy = 2u * node_y + ((lane >> 1) & 1u), chz = 2u * node_z + (lane & 1u);
+        uint2 r = make_uint2(0u, 0u);
+        float mind2 = INFINITY;
+        bool admit = false;
+        if (expand && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl)) {
+            r = table[table_index(gp, cl, chx, chy, chz)];
+            if (r.y > r.x) {
+                const float pitch = ldexpf(gp.h, cl);
+                const float lo[3] = {gp.gmin[0] + (float)chx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
+                const float qq[3] = {q.x, q.y, q.z};
+                mind2 = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
+                    mind2 += d * d;
+                }
+                admit = mind2 * 0.9999f <= thr;
+            }
+        }
+        const unsigned adm = __ballot_sync(FULL_MASK, admit);
+        if (adm) {
+            const int nadm = __popc(adm);
+            // position among the admitted children, nearest first: a 32-lane bitonic sort of (distance, lane) keys
+            // (distances are non-negative floats: their bit patterns order like the values)
+            unsigned long long key = admit ? (((unsigned long long)__float_as_uint(mind2) << 32) | lane) : ~0ull;
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(FULL_MASK, key, j2);
+                    const bool up = (lane & (unsigned)k2) == 0u;
+                    const bool lower = (lane & (unsigned)j2) == 0u;
+                    key = (lower == up) ? (key < other ? key : other) : (key < other ? other : key);
+                }
+            }
+            // lane i now holds the i-th nearest admitted child's (distance, source lane); fetch that child and store it
+            const int src = (int)(key & 31u);
+            FarNode ch;
+            ch.pb = __shfl_sync(FULL_MASK, r.x, src);
+            ch.pe = __shfl_sync(FULL_MASK, r.y, src);
+            ch.xy = __shfl_sync(FULL_MASK, chx | (chy << 16), src);
+            ch.zl = __shfl_sync(FULL_MASK, chz | ((uint32_t)cl << 16), src);
+            ch.mind2 = __shfl_sync(FULL_MASK, mind2, src);
+            if ((int)lane < nadm) stack[sp + nadm - 1 - (int)lane] = ch; // farthest deepest, nearest on top
+            sp += nadm;
+        }
+        __syncwarp();
     }
 }
 
