@@ -344,6 +344,131 @@ int cwipc_cuda_knn_query(cwipc_pointcloud *pc, int kNeighbors, int nquery, float
     });
 }
 
+// ---- device-resident per-point distances of a slab (so that only the few open queries ever reach the host) ----
+struct cwipc_cuda_distances {
+    int dev = 0;
+    size_t n = 0;          // queries
+    Scratch *mean = nullptr;   // float[n], owned (plain cudaMallocAsync blocks: they outlive the call that made them)
+    Scratch *open_idx = nullptr; // uint32[nopen]
+    size_t nopen = 0;
+};
+
+namespace {
+// scratch that must survive the API call: bypass the per-call arena by allocating on a null-arena path
+Scratch *persistent_scratch(size_t bytes, cudaStream_t s) {
+    auto *sc = new Scratch();
+    sc->p = dmalloc(bytes, s);
+    sc->s = s;
+    sc->arena = false;
+    return sc;
+}
+} // namespace
+
+cwipc_cuda_distances *cwipc_cuda_knn_query_open(cwipc_pointcloud *pc, int kNeighbors, int nquery, float x_lo, float x_hi, int *nopen) {
+    if (pc == nullptr || nquery < 0 || nopen == nullptr) return nullptr;
+    return guarded<cwipc_cuda_distances *>("cwipc_cuda_knn_query_open", nullptr, [&]() -> cwipc_cuda_distances * {
+        StoragePtr in = storage_of(pc, "cwipc_cuda_knn_query_open");
+        if (!in || (size_t)nquery > in->count) return nullptr;
+        DeviceGuard g(in->dev);
+        cudaStream_t s = thread_stream(in->dev);
+        auto *h = new cwipc_cuda_distances();
+        h->dev = in->dev;
+        h->n = (size_t)nquery;
+        *nopen = 0;
+        if (nquery == 0) return h;
+        in->acquire_for_read(s);
+        h->mean = persistent_scratch((size_t)nquery * sizeof(float), s);
+        h->open_idx = persistent_scratch((size_t)nquery * sizeof(uint32_t), s);
+        try {
+            if (in->count > (size_t)kNeighbors) {
+                Scratch d(in->count * sizeof(float), s), kth(in->count * sizeof(float), s);
+                float box[6];
+                knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), bounds_of(*in, box), d.as<float>(), in->dev, s, kth.as<float>(), (size_t)nquery);
+                CWCU_CHECK(cudaMemcpyAsync(h->mean->p, d.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                h->nopen = mark_open_queries(in->d_pts, kth.as<float>(), (size_t)nquery, x_lo, x_hi, h->open_idx->as<uint32_t>(), in->dev, s);
+            } else { // fewer points than neighbours here: every query is open
+                h->nopen = mark_open_queries(in->d_pts, nullptr, (size_t)nquery, x_lo, x_hi, h->open_idx->as<uint32_t>(), in->dev, s);
+            }
+        } catch (...) {
+            in->release_after_read(s);
+            delete h->mean;
+            delete h->open_idx;
+            delete h;
+            throw;
+        }
+        in->release_after_read(s);
+        *nopen = (int)h->nopen;
+        return h;
+    });
+}
+
+// indices (into the first nquery points) and coordinates of the open queries, to host
+int cwipc_cuda_distances_open(cwipc_cuda_distances *h, cwipc_pointcloud *pc, uint32_t *idx, struct cwipc_point *points) {
+    if (h == nullptr || pc == nullptr) return -1;
+    return guarded<int>("cwipc_cuda_distances_open", -1, [&]() -> int {
+        if (h->nopen == 0) return 0;
+        StoragePtr in = storage_of(pc, "cwipc_cuda_distances_open");
+        if (!in) return -1;
+        DeviceGuard g(h->dev);
+        cudaStream_t s = thread_stream(h->dev);
+        in->acquire_for_read(s);
+        Scratch q(h->nopen * sizeof(cwipc_point), s);
+        gather_points(in->d_pts, h->open_idx->as<uint32_t>(), h->nopen, q.as<cwipc_point>(), s);
+        if (idx) CWCU_CHECK(cudaMemcpyAsync(idx, h->open_idx->p, h->nopen * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (points) CWCU_CHECK(cudaMemcpyAsync(points, q.p, h->nopen * sizeof(cwipc_point), cudaMemcpyDeviceToHost, s));
+        in->release_after_read(s);
+        stream_sync(s);
+        return (int)h->nopen;
+    });
+}
+
+// mean[idx[i]] = values[i] for the open queries (values in the order cwipc_cuda_distances_open returned them)
+int cwipc_cuda_distances_patch(cwipc_cuda_distances *h, const float *values, int n) {
+    if (h == nullptr || n < 0 || (size_t)n != h->nopen || (n > 0 && values == nullptr)) return -1;
+    return guarded<int>("cwipc_cuda_distances_patch", -1, [&]() -> int {
+        if (n == 0) return 0;
+        DeviceGuard g(h->dev);
+        cudaStream_t s = thread_stream(h->dev);
+        Scratch v((size_t)n * sizeof(float), s);
+        CWCU_CHECK(cudaMemcpyAsync(v.p, values, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+        scatter_floats(v.as<float>(), h->open_idx->as<uint32_t>(), (size_t)n, h->mean->as<float>(), s);
+        stream_sync(s);
+        return n;
+    });
+}
+
+int cwipc_cuda_distances_stats(cwipc_cuda_distances *h, double sums[2]) {
+    if (h == nullptr || sums == nullptr) return -1;
+    return guarded<int>("cwipc_cuda_distances_stats", -1, [&]() -> int {
+        DeviceGuard g(h->dev);
+        distance_stats(h->n ? h->mean->as<float>() : nullptr, h->n, sums, thread_stream(h->dev));
+        return 0;
+    });
+}
+
+cwipc_pointcloud *cwipc_cuda_distances_filter(cwipc_pointcloud *pc, cwipc_cuda_distances *h, double threshold) {
+    if (h == nullptr) return nullptr;
+    return unary_filter("cwipc_cuda_distances_filter", pc, [&](const StoragePtr &in, int dev, cudaStream_t s) -> StoragePtr {
+        if (h->n != in->count) throw CudaError{cudaErrorInvalidValue, "one distance per point is required"};
+        Predicate p;
+        p.kind = PredKind::DistanceAtMost;
+        p.dist = h->n ? h->mean->as<float>() : nullptr;
+        p.threshold = threshold;
+        return compact_to_new(in, p, dev, s);
+    });
+}
+
+void cwipc_cuda_distances_free(cwipc_cuda_distances *h) {
+    if (h == nullptr) return;
+    try {
+        DeviceGuard g(h->dev);
+        delete h->mean;
+        delete h->open_idx;
+    } catch (...) {
+    }
+    delete h;
+}
+
 int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, int nq, int kNeighbors, float *lists) {
     if (pc == nullptr || nq < 0 || (nq > 0 && (queries == nullptr || lists == nullptr))) return -1;
     return guarded<int>("cwipc_cuda_knn_lists", -1, [&]() -> int {

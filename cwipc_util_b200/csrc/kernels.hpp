@@ -68,6 +68,11 @@ void knn_merge_lists(const float *d_lists, size_t nlists, size_t nq, int k, floa
 // sum d, sum (float)(d*d), both in double (synchronises the stream)
 void distance_stats(const float *d_dist, size_t n, double out[2], cudaStream_t s);
 double outlier_threshold(double sum, double sq, double n, float stddev_mul);
+// Slab protocol: indices i < nquery whose (k+1)-th neighbour sphere (kth2[i], squared) is not strictly inside the covered
+// interval (x_lo, x_hi); kth2 == nullptr marks every query.  Returns their number (synchronises the stream).
+size_t mark_open_queries(const cwipc_point *pts, const float *kth2, size_t nquery, float x_lo, float x_hi, uint32_t *open_idx, int dev, cudaStream_t s);
+void gather_points(const cwipc_point *pts, const uint32_t *idx, size_t n, cwipc_point *out, cudaStream_t s);
+void scatter_floats(const float *values, const uint32_t *idx, size_t n, float *out, cudaStream_t s);
 
 // ---- runtime.cu ----------------------------------------------------------------------------
 void flush_l2(int dev, cudaStream_t s);

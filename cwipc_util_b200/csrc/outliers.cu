@@ -952,6 +952,61 @@ void distance_stats(const float *d_dist, size_t n, double out[2], cudaStream_t s
     }
 }
 
+namespace {
+__global__ void __launch_bounds__(256) mark_open_kernel(const cwipc_point *__restrict__ pts, const float *__restrict__ kth2, uint32_t nquery, float x_lo, float x_hi,
+                                                         uint32_t *__restrict__ open_idx, uint32_t *__restrict__ counter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool open = false;
+    if (i < nquery) {
+        open = true;
+        if (kth2) {
+            const double x = (double)ld_point(pts, i).x;
+            const double rk = sqrt((double)kth2[i]) * (1.0 + 1e-6);
+            open = !(x - rk > (double)x_lo && x + rk < (double)x_hi); // also open when kth2 is +inf or NaN
+        }
+    }
+    const unsigned m = __ballot_sync(FULL_MASK, open);
+    if (m == 0u) return;
+    const unsigned lane = lane_id();
+    uint32_t first = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) first = atomicAdd(counter, (uint32_t)__popc(m));
+    first = __shfl_sync(FULL_MASK, first, __ffs(m) - 1);
+    if (open) open_idx[first + __popc(m & lanemask_lt())] = i;
+}
+__global__ void __launch_bounds__(256) gather_points_kernel(const cwipc_point *__restrict__ pts, const uint32_t *__restrict__ idx, uint32_t n, cwipc_point *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st_point(out, i, ld_point(pts, idx[i]));
+}
+__global__ void __launch_bounds__(256) scatter_floats_kernel(const float *__restrict__ values, const uint32_t *__restrict__ idx, uint32_t n, float *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[idx[i]] = values[i];
+}
+} // namespace
+
+size_t mark_open_queries(const cwipc_point *pts, const float *kth2, size_t nquery, float x_lo, float x_hi, uint32_t *open_idx, int dev, cudaStream_t s) {
+    (void)dev;
+    if (nquery == 0) return 0;
+    Scratch counter(sizeof(uint32_t), s);
+    CWCU_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(uint32_t), s));
+    launch("mark_open_kernel", s, 20 * nquery, [&] {
+        mark_open_kernel<<<(unsigned)div_up(nquery, 256), 256, 0, s>>>(pts, kth2, (uint32_t)nquery, x_lo, x_hi, open_idx, counter.as<uint32_t>());
+    });
+    uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
+    CWCU_CHECK(cudaMemcpyAsync(h, counter.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    return *h;
+}
+
+void gather_points(const cwipc_point *pts, const uint32_t *idx, size_t n, cwipc_point *out, cudaStream_t s) {
+    if (n == 0) return;
+    launch("gather_points_kernel", s, 36 * n, [&] { gather_points_kernel<<<(unsigned)div_up(n, 256), 256, 0, s>>>(pts, idx, (uint32_t)n, out); });
+}
+
+void scatter_floats(const float *values, const uint32_t *idx, size_t n, float *out, cudaStream_t s) {
+    if (n == 0) return;
+    launch("scatter_floats_kernel", s, 12 * n, [&] { scatter_floats_kernel<<<(unsigned)div_up(n, 256), 256, 0, s>>>(values, idx, (uint32_t)n, out); });
+}
+
 // ref: pcl statistical_outlier_removal.hpp -- mean, unbiased variance, threshold in double
 double outlier_threshold(double sum, double sq, double n, float stddev_mul) {
     const double mean = sum / n;

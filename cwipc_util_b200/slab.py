@@ -141,9 +141,6 @@ class CudaOps:
     def cellsize(self, pc) -> float:
         return pc.cellsize()
 
-    def to_numpy(self, pc) -> numpy.ndarray:
-        return pc.get_numpy_array()
-
     def replay(self, pc, cellsize: float, state: numpy.ndarray):
         st = self.u.cwipc_cuda_octree_state.from_array(state)
         bounds = self.u.octree_replay(pc, cellsize, st)
@@ -159,8 +156,14 @@ class CudaOps:
     def downsample_planned(self, pc, voxelsize: float, state: numpy.ndarray, bounds: numpy.ndarray):
         return self.u.downsample_planned(pc, voxelsize, self.u.cwipc_cuda_octree_state.from_array(state), bounds)
 
-    def knn_query(self, pc, k: int, nquery: int):
-        return self.u.knn_query(pc, k, nquery)
+    def knn_open(self, pc, k: int, nquery: int, x_lo: float, x_hi: float):
+        """Distances of the first nquery points of `pc` (kept on the device) + indices and coordinates of the open queries."""
+        d = self.u.cuda_distances(pc, k, nquery, x_lo, x_hi)
+        idx, pts = d.open_queries()
+        return d, idx, pts
+
+    def keep_all(self, pc):
+        return self.u.cwipc_tilefilter(pc, 0)
 
     def knn_lists(self, pc, queries: numpy.ndarray, k: int) -> numpy.ndarray:
         return self.u.knn_lists(pc, queries, k)
@@ -168,14 +171,19 @@ class CudaOps:
     def merge_lists(self, lists: numpy.ndarray, k: int) -> numpy.ndarray:
         return self.u.knn_merge_lists(lists, k)[0]
 
-    def distance_stats(self, dist: numpy.ndarray):
-        return self.u.distance_stats(dist)
+    def patch(self, d, values: numpy.ndarray) -> None:
+        d.patch(values)
+
+    def distance_stats(self, d):
+        return d.stats()
 
     def threshold(self, total: float, sq: float, n: float, mul: float) -> float:
         return self.u.outlier_threshold(total, sq, n, mul)
 
-    def filter_by_distance(self, pc, dist: numpy.ndarray, thr: float):
-        return self.u.filter_by_distance(pc, dist, thr)
+    def filter_by_distance(self, pc, d, thr: float):
+        out = d.filter(pc, thr)
+        d.free()
+        return out
 
     # ---- wire: device buffers straight into NCCL ---------------------------------------------------------
     def to_wire(self, pc):
@@ -284,17 +292,16 @@ def slab_remove_outliers(pc, k: int, mul: float, comm: TorchComm, ops, halo: Opt
     """cwipc_remove_outliers(whole cloud, perTile=False) on the partitioned cloud; returns this rank's survivors."""
     G, r = comm.size, comm.rank
     n_local = ops.count(pc)
-    pts = ops.to_numpy(pc)
-    x = pts["x"].astype(numpy.float64)
+    _, b = ops.replay(pc, 1.0, numpy.zeros(8))  # only the bounding box is used here
     ext = numpy.zeros((G, 2))
-    ext[r] = (x.min(), x.max()) if n_local else (numpy.inf, -numpy.inf)
+    ext[r] = (b[0], b[3]) if n_local else (numpy.inf, -numpy.inf)
     big = 3.0e38  # all-reduce friendly stand-in for +-inf
     ext = numpy.clip(ext, -big, big)
     ext = comm.allreduce(ext.reshape(-1), "SUM").reshape(G, 2)
     counts = comm.allreduce((numpy.arange(G) == r) * float(n_local), "SUM")
     n_total = int(counts.sum())
     if n_total <= k:  # the reference reads past FLANN's results here; defined as keep-all (see outliers.cu)
-        return ops.filter_by_distance(pc, numpy.zeros(n_local, numpy.float32), float("inf"))
+        return ops.keep_all(pc)
     cs = comm.allreduce(numpy.array([float(ops.cellsize(pc))]), "MAX")[0]
     if halo is None:
         if cs > 0:
@@ -317,20 +324,15 @@ def slab_remove_outliers(pc, k: int, mul: float, comm: TorchComm, ops, halo: Opt
     incoming = _exchange_points(comm, ops, outgoing, timestamp, float(ops.cellsize(pc)))
     combined = ops.join([pc] + incoming) if incoming else pc
 
-    # 2. local queries against local + halo points
-    if n_local and ops.count(combined) > k:
-        mean, kth2 = ops.knn_query(combined, k, n_local)
-    else:
-        mean, kth2 = numpy.zeros(n_local, numpy.float32), numpy.full(n_local, numpy.inf, numpy.float32)
+    # 2. local queries against local + halo points; the distances stay on the device, only the queries whose
+    #    neighbourhood leaves the covered interval come back
     others = [q for q in range(G) if q != r and counts[q] > 0]
     lo_lim = ext[r, 0] - H if any(ext[q, 0] < ext[r, 0] - H for q in others) else -numpy.inf
     hi_lim = ext[r, 1] + H if any(ext[q, 1] > ext[r, 1] + H for q in others) else numpy.inf
-    rk = numpy.sqrt(kth2.astype(numpy.float64)) * (1.0 + 1e-6)
-    final = (x - rk > lo_lim) & (x + rk < hi_lim)
-    open_idx = numpy.nonzero(~final)[0]
+    dists, open_idx, open_pts = ops.knn_open(combined, k, n_local, float(lo_lim), float(hi_lim))
 
     # 3. the open queries: every rank answers from its own points, the owner merges
-    all_q = comm.allgather_bytes(pts[open_idx])
+    all_q = comm.allgather_bytes(open_pts)
     nq = [len(a) for a in all_q]
     if sum(nq):
         queries = numpy.concatenate(all_q)
@@ -339,11 +341,10 @@ def slab_remove_outliers(pc, k: int, mul: float, comm: TorchComm, ops, halo: Opt
         if nq[r]:
             off = sum(nq[:r])
             mine = numpy.stack([blk[off:off + nq[r]] for blk in all_lists])
-            mean = mean.copy()
-            mean[open_idx] = ops.merge_lists(mine, k)
+            ops.patch(dists, ops.merge_lists(mine, k))
 
     # 4. global statistics, local threshold
-    s, sq = ops.distance_stats(mean) if n_local else (0.0, 0.0)
+    s, sq = ops.distance_stats(dists) if n_local else (0.0, 0.0)
     tot = comm.allreduce(numpy.array([s, sq, float(n_local)]), "SUM")
     thr = ops.threshold(float(tot[0]), float(tot[1]), float(tot[2]), mul)
-    return ops.filter_by_distance(pc, mean, thr)
+    return ops.filter_by_distance(pc, dists, thr)

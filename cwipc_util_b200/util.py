@@ -159,6 +159,12 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
         "cwipc_cuda_distance_stats": ([ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_outlier_threshold": ([ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float], ctypes.c_double),
         "cwipc_cuda_filter_by_distance": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double], cwipc_pointcloud_p),
+        "cwipc_cuda_knn_query_open": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p], ctypes.c_void_p),
+        "cwipc_cuda_distances_open": ([ctypes.c_void_p, cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_distances_patch": ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int], ctypes.c_int),
+        "cwipc_cuda_distances_stats": ([ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_distances_filter": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_double], cwipc_pointcloud_p),
+        "cwipc_cuda_distances_free": ([ctypes.c_void_p], None),
         "cwipc_cuda_sort_u64": ([ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int], ctypes.c_int),
         "cwipc_cuda_timer_create": ([], ctypes.c_void_p),
         "cwipc_cuda_timer_destroy": ([ctypes.c_void_p], None),
@@ -591,3 +597,47 @@ def sort_u64(words: numpy.ndarray, begin_bit: int, end_bit: int) -> numpy.ndarra
     if cwipc_util_dll_load().cwipc_cuda_sort_u64(w.ctypes.data, len(w), begin_bit, end_bit) != 0:
         raise CwipcError("cwipc_cuda_sort_u64 failed")
     return w
+
+
+class cuda_distances:
+    """Device-resident mean kNN distances of a slab's points (include/cwipc_util_cuda.h: cwipc_cuda_distances)."""
+
+    def __init__(self, pc: cwipc_pointcloud_wrapper, kNeighbors: int, nquery: int, x_lo: float, x_hi: float):
+        nopen = ctypes.c_int(0)
+        self._h = cwipc_util_dll_load().cwipc_cuda_knn_query_open(pc.as_cwipc_p(), kNeighbors, nquery, x_lo, x_hi, ctypes.byref(nopen))
+        if not self._h:
+            raise CwipcError("cwipc_cuda_knn_query_open failed")
+        self.nopen = nopen.value
+        self._pc = pc
+
+    def __del__(self):
+        self.free()
+
+    def free(self) -> None:
+        if getattr(self, "_h", None):
+            cwipc_util_dll_load().cwipc_cuda_distances_free(self._h)
+            self._h = None
+
+    def open_queries(self):
+        idx = numpy.zeros(self.nopen, numpy.uint32)
+        pts = numpy.zeros(self.nopen, cwipc_point_numpy_dtype)
+        if self.nopen and cwipc_util_dll_load().cwipc_cuda_distances_open(self._h, self._pc.as_cwipc_p(), idx.ctypes.data, pts.ctypes.data) < 0:
+            raise CwipcError("cwipc_cuda_distances_open failed")
+        return idx, pts
+
+    def patch(self, values: numpy.ndarray) -> None:
+        v = numpy.ascontiguousarray(values, numpy.float32)
+        if cwipc_util_dll_load().cwipc_cuda_distances_patch(self._h, v.ctypes.data, len(v)) < 0:
+            raise CwipcError("cwipc_cuda_distances_patch failed")
+
+    def stats(self):
+        sums = numpy.zeros(2, numpy.float64)
+        if cwipc_util_dll_load().cwipc_cuda_distances_stats(self._h, sums.ctypes.data) != 0:
+            raise CwipcError("cwipc_cuda_distances_stats failed")
+        return float(sums[0]), float(sums[1])
+
+    def filter(self, pc: cwipc_pointcloud_wrapper, threshold: float) -> cwipc_pointcloud_wrapper:
+        rv = cwipc_util_dll_load().cwipc_cuda_distances_filter(pc.as_cwipc_p(), self._h, threshold)
+        if not rv:
+            raise CwipcError("cwipc_cuda_distances_filter failed")
+        return cwipc_pointcloud_wrapper(rv)

@@ -334,6 +334,18 @@ _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_from_device_points(const void *d
 /* First pass of cwipc_remove_outliers for the first nquery points against ALL points of the cloud (the rest
  * being halo points): mean distance to the k nearest and the (k+1)-th smallest squared distance, nquery floats each. */
 _CWIPC_UTIL_EXPORT int cwipc_cuda_knn_query(cwipc_pointcloud *pc, int kNeighbors, int nquery, float *mean, float *kth2);
+/* The same first pass with the result kept on the device: mean distances of the first nquery points, plus the list of
+ * "open" queries, i.e. those whose (k+1)-th neighbour sphere is not strictly inside the covered interval (x_lo, x_hi) of
+ * this part and therefore have to be completed with the other parts' points.  Only the open queries ever reach the host. */
+typedef struct cwipc_cuda_distances cwipc_cuda_distances;
+_CWIPC_UTIL_EXPORT cwipc_cuda_distances *cwipc_cuda_knn_query_open(cwipc_pointcloud *pc, int kNeighbors, int nquery, float x_lo, float x_hi, int *nopen);
+/* indices and coordinates of the open queries (nopen entries each, either may be NULL) */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_distances_open(cwipc_cuda_distances *d, cwipc_pointcloud *pc, uint32_t *idx, struct cwipc_point *points);
+/* overwrite the mean distance of the open queries, in the order cwipc_cuda_distances_open listed them */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_distances_patch(cwipc_cuda_distances *d, const float *values, int n);
+_CWIPC_UTIL_EXPORT int cwipc_cuda_distances_stats(cwipc_cuda_distances *d, double sums[2]);
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_distances_filter(cwipc_pointcloud *pc, cwipc_cuda_distances *d, double threshold);
+_CWIPC_UTIL_EXPORT void cwipc_cuda_distances_free(cwipc_cuda_distances *d);
 /* The k+1 smallest squared distances (ascending, +inf padded) from nq arbitrary query points to the cloud: lists[nq][k+1]. */
 _CWIPC_UTIL_EXPORT int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, int nq, int kNeighbors, float *lists);
 /* Merge lists[nlists][nq][k+1] (one list per part of the cloud) into the mean distance / (k+1)-th squared distance. */

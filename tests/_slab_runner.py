@@ -64,9 +64,6 @@ class NumpyOps:
     def cellsize(self, pc):
         return pc.cellsize
 
-    def to_numpy(self, pc):
-        return pc.pts
-
     def replay(self, pc, cellsize, state):
         st = numpy.array(state, numpy.float64)
         if len(pc.pts) == 0:
@@ -103,9 +100,23 @@ class NumpyOps:
         out["tile"] = numpy.bitwise_or.reduceat(p["tile"][order], start)
         return NpCloud(out, float(cs))
 
-    def knn_query(self, pc, k, nquery):
-        l = _lists(pc.pts[:nquery], pc.pts, k)
-        return _mean_from_lists(l, k), l[:, k].copy()
+    def knn_open(self, pc, k, nquery, x_lo, x_hi):
+        q = pc.pts[:nquery]
+        if len(pc.pts) > k:
+            l = _lists(q, pc.pts, k)
+            mean, kth2 = _mean_from_lists(l, k), l[:, k]
+        else:
+            mean, kth2 = numpy.zeros(nquery, numpy.float32), numpy.full(nquery, numpy.inf, numpy.float32)
+        x = q["x"].astype(numpy.float64)
+        rk = numpy.sqrt(kth2.astype(numpy.float64)) * (1.0 + 1e-6)
+        open_idx = numpy.nonzero(~((x - rk > x_lo) & (x + rk < x_hi)))[0].astype(numpy.uint32)
+        return {"mean": mean.copy(), "idx": open_idx}, open_idx, q[open_idx]
+
+    def keep_all(self, pc):
+        return pc
+
+    def patch(self, d, values):
+        d["mean"][d["idx"]] = values
 
     def knn_lists(self, pc, queries, k):
         return _lists(queries, pc.pts, k)
@@ -115,14 +126,14 @@ class NumpyOps:
         return _mean_from_lists(merged, k)
 
     def distance_stats(self, dist):
-        d = dist.astype(numpy.float32)
+        d = dist["mean"].astype(numpy.float32)
         return float(d.astype(numpy.float64).sum()), float((d * d).astype(numpy.float64).sum())
 
     def threshold(self, total, sq, n, mul):
         return total / n + mul * math.sqrt((sq - total * total / n) / (n - 1.0))
 
     def filter_by_distance(self, pc, dist, thr):
-        return NpCloud(pc.pts[~(dist.astype(numpy.float64) > thr)], pc.cellsize)
+        return NpCloud(pc.pts[~(dist["mean"].astype(numpy.float64) > thr)], pc.cellsize)
 
     def to_wire(self, pc):
         import torch
