@@ -35,9 +35,9 @@ import numpy as np
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-POINTS_PER_FRAME = 1000 * 1000
+POINTS_PER_FRAME = int(os.environ.get("BENCH_POINTS", 1000 * 1000))   # BENCH_POINTS: diagnostic only (host-bound or GPU-bound?)
 VOXEL = 0.01
-K, STDDEV = 30, 1.0
+K, STDDEV = int(os.environ.get("BENCH_K", 30)), 1.0   # BENCH_K: diagnostic only
 FRAMES_PER_GPU = 30          # 240 frames / 8 GPUs
 WORKERS = 15                 # host threads (one CUDA stream each) feeding one GPU; divides the 30 frames of a step
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent

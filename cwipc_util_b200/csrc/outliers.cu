@@ -217,13 +217,13 @@ struct FarEntry {
 // shared loads.  Per lane, distances below the running (k+1)-th best are parked in a shared-memory
 // column and merged into a sorted register array 16 at a time by bitonic networks, so the
 // per-candidate cost is a distance, a compare and a predicated store.
-constexpr int KT_WARPS = 8;
+constexpr int KT_WARPS = 2;  // small blocks: a block's registers and shared memory stay allocated until its slowest warp is done
 constexpr int KT_THREADS = KT_WARPS * 32;
 constexpr int KT_CH = 128;     // candidates per stage
 constexpr int KT_STAGES = 2;
 constexpr int KT_MAXR = 216;   // cells of the largest candidate box: 6x6x6 (a 4-cell group span + rc <= 1 on both sides)
 constexpr int KT_BUF = 16;     // parked distances per lane
-constexpr int KT_BLOCKS_PER_SM = 3; // register budget 85/thread: more resident warps hide the scan's latency
+constexpr int KT_BLOCKS_PER_SM = 12; // register budget 85/thread (24 warps per SM): more resident warps hide the scan's latency
 
 struct __align__(128) KnnWarpSmem {
     Point16 cand[KT_STAGES][KT_CH]; // 4096 B
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
 // run of points), nearest child first, pruned by the running (k+1)-th best.  The best list lives
 // across the lanes (element e in lane e%32, register e/32) and absorbs 32 new distances at a time
 // through warp-shuffle bitonic networks.
-constexpr int KF_WARPS = 4;
+constexpr int KF_WARPS = 2;
 constexpr int KF_THREADS = KF_WARPS * 32;
 constexpr int KF_STACK = 416; // four nodes are expanded per step: <= 28 * top_level + 32 open nodes with top_level <= 13
 
@@ -834,7 +834,7 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     if (gp.top_level == 0) return; // one cell spans the cloud: the main pass is exact for every query
     constexpr int KPL = KCAP > 32 ? 2 : 1;
     launch("knn_far_kernel", s, (size_t)0, [&] {
-        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 4, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, far_leaf_points());
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 8, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, far_leaf_points());
     });
 }
 
@@ -921,7 +921,7 @@ void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, si
     }
     KnnIndex ix;
     build_index(ix, in, n, k, hint_spacing, bounds, dev, s);
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nq, (size_t)KF_WARPS), (size_t)sm_count(dev) * 4));
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nq, (size_t)KF_WARPS), (size_t)sm_count(dev) * 8));
     launch("knn_list_kernel", s, (size_t)0, [&] {
         if (kk <= 32)
             knn_list_kernel<1><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, (uint32_t)nq, d_lists, far_leaf_points());

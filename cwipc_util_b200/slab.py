@@ -56,6 +56,13 @@ class TorchComm:
         self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op), group=self.group)
         return t.cpu().numpy()
 
+    def gather_rows(self, row) -> numpy.ndarray:
+        """Every rank contributes one row of floats; all get the size x len(row) matrix (one collective)."""
+        row = numpy.asarray(row, numpy.float64)
+        m = numpy.zeros((self.size, len(row)))
+        m[self.rank] = row
+        return self.allreduce(m.reshape(-1), "SUM").reshape(self.size, len(row))
+
     def broadcast(self, a: numpy.ndarray, src: int) -> numpy.ndarray:
         t = self._t(numpy.asarray(a, numpy.float64))
         self.dist.broadcast(t, src=src, group=self.group)
@@ -244,27 +251,31 @@ def slab_downsample(pc, voxelsize: float, comm: TorchComm, ops, timestamp: int =
     """cwipc_downsample of the cloud whose parts are the ranks' `pc` (rank order); returns this rank's part of the result."""
     G, r = comm.size, comm.rank
     octree = not (voxelsize < 0)
-    cs = numpy.float32(abs(voxelsize))
-    cs = numpy.float32(comm.allreduce(numpy.array([max(float(cs), float(ops.cellsize(pc)))]), "MAX")[0])  # ref: src/cwipc_filters.cpp:103-107
 
-    # 1. octree box replay, rank by rank, and the bounding box of the whole cloud
+    # 0. one collective for everything that is known locally: cellsize metadata, point count, bounding box
+    _, b = ops.replay(pc, 1.0, numpy.zeros(8))  # bounding box of this part (the octree state of this call is not used)
+    info = comm.gather_rows([float(ops.cellsize(pc)), float(ops.count(pc))] + list(b))
+    have = info[:, 1] > 0
+    cs = numpy.float32(max(abs(voxelsize), float(info[:, 0].max())))  # ref: src/cwipc_filters.cpp:103-107
+    if not have.any():  # every part is empty
+        return ops.downsample_planned(pc, voxelsize, numpy.zeros(8), numpy.zeros(6))
+    gmin = info[have, 2:5].min(axis=0)
+    gmax = info[have, 5:8].max(axis=0)
+    xmins = info[:, 2]
+
+    # 1. octree box replay, rank by rank (the box grows with the points IN ORDER), then broadcast
     state = numpy.zeros(8)
-    if octree and r > 0:
-        state = comm.recv(8, r - 1)
-    state, b = ops.replay(pc, float(cs), state)
-    if octree and r < G - 1:
-        comm.send(state, r + 1)
     if octree:
-        state = comm.broadcast(state, G - 1)
-    gmin = comm.allreduce(b[:3], "MIN")
-    gmax = comm.allreduce(b[3:], "MAX")
-    if not numpy.isfinite(gmin[0]):  # every part is empty
-        return ops.downsample_planned(pc, voxelsize, state, numpy.zeros(6))
+        if r > 0:
+            state = comm.recv(8, r - 1)
+        state, _ = ops.replay(pc, float(cs), state)
+        if r < G - 1:
+            comm.send(state, r + 1)
+        if G > 1:
+            state = comm.broadcast(state, G - 1)
 
     # 2. voxel columns -> owners; boundary points move to the owner of their column
     inv = numpy.float32(1.0) / cs
-    xmins = comm.allreduce(numpy.where(numpy.arange(G) == r, b[0], 0.0) if numpy.isfinite(b[0]) else numpy.zeros(G), "SUM")
-    have = comm.allreduce((numpy.arange(G) == r) * float(numpy.isfinite(b[0])), "SUM") > 0
     splits = numpy.full(G + 1, numpy.inf)  # columns [splits[q], splits[q+1]) belong to rank q
     splits[0] = -numpy.inf
     for q in range(1, G):
@@ -293,16 +304,13 @@ def slab_remove_outliers(pc, k: int, mul: float, comm: TorchComm, ops, halo: Opt
     G, r = comm.size, comm.rank
     n_local = ops.count(pc)
     _, b = ops.replay(pc, 1.0, numpy.zeros(8))  # only the bounding box is used here
-    ext = numpy.zeros((G, 2))
-    ext[r] = (b[0], b[3]) if n_local else (numpy.inf, -numpy.inf)
-    big = 3.0e38  # all-reduce friendly stand-in for +-inf
-    ext = numpy.clip(ext, -big, big)
-    ext = comm.allreduce(ext.reshape(-1), "SUM").reshape(G, 2)
-    counts = comm.allreduce((numpy.arange(G) == r) * float(n_local), "SUM")
+    info = comm.gather_rows([float(ops.cellsize(pc)), float(n_local), b[0] if n_local else numpy.inf, b[3] if n_local else -numpy.inf])
+    counts = info[:, 1]
+    ext = info[:, 2:4]
     n_total = int(counts.sum())
     if n_total <= k:  # the reference reads past FLANN's results here; defined as keep-all (see outliers.cu)
         return ops.keep_all(pc)
-    cs = comm.allreduce(numpy.array([float(ops.cellsize(pc))]), "MAX")[0]
+    cs = float(info[:, 0].max())
     if halo is None:
         if cs > 0:
             halo = 3.0 * cs * math.sqrt((k + 1) / math.pi)
