@@ -382,9 +382,18 @@ def run_ours(args):
     if prof:
         name, rec = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
         achieved = rec["bytes"] / (rec["total_ms"] / 1e3) / 1e9 if rec["total_ms"] > 0 else 0.0
-        traffic = None
+        traffic, issue = None, None
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(name)
+            tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+            traffic = tj.get(name)
+            winst = tj.get("_warp_instructions", {}).get(name)
+            if winst and rec["total_ms"] > 0:
+                # instruction-issue roofline of the same launches: warp instructions per launch (ncu smsp__inst_executed.sum)
+                # over the measured launch time, against 148 SMs x 4 schedulers x 1 instruction per clock at the max SM clock
+                per_s = winst / (rec["total_ms"] / 1e3 / max(1, rec["launches"]))
+                peak_issue = 148 * 4 * 1.965e9
+                issue = {"warp_inst_per_launch": winst, "achieved_Ginst_per_s": round(per_s / 1e9, 1), "peak_Ginst_per_s": round(peak_issue / 1e9, 1),
+                         "frac": round(per_s / peak_issue, 4)}
         except Exception:
             pass
         step_kernel_ms = sum(r["total_ms"] for r in prof.values())
@@ -394,7 +403,7 @@ def run_ours(args):
             kernels[k] = {"launches_per_frame": round(v["launches"] / nprof, 2), "us_per_launch": round(v["total_ms"] * 1e3 / max(1, v["launches"]), 2),
                           "GBps": round(gbs, 1), "frac": round(gbs / peak, 4), "share": round(v["total_ms"] / step_kernel_ms, 3)}
         roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": traffic, "peak_source": peak_src, "launches": rec["launches"], "avg_launch_us": round(rec["total_ms"] * 1e3 / max(1, rec["launches"]), 2),
+                    "traffic": traffic, "issue": issue, "peak_source": peak_src, "launches": rec["launches"], "avg_launch_us": round(rec["total_ms"] * 1e3 / max(1, rec["launches"]), 2),
                     "algorithmic_bytes_per_launch": int(rec["bytes"] / max(1, rec["launches"])), "share_of_step_kernel_time": round(rec["total_ms"] / step_kernel_ms, 3),
                     "how": f"{nprof} of the step's frames replayed on one stream, CUDA events around every launch (cwipc_cuda_profile_*)",
                     "note": "the kNN kernels are instruction-issue bound (exact top-(k+1) selection over ~300 candidates per query), not HBM bound: "
