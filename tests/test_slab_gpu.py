@@ -71,6 +71,20 @@ def test_slabs_unordered_parts_and_tiny_halo(cw, tmp_path):
     assert abs(single.count() - sum(len(p) for p in sorn)) <= 2
 
 
+def test_slabs_with_an_empty_part(cw, tmp_path):
+    parts = make_parts(20000, 2, seed=77)
+    parts = [parts[0], parts[1][:0], parts[1]]  # rank 1 holds nothing
+    args = dict(voxelsize=0.02, k=10, mul=1.0, cellsize=0.0)
+    dsn, sorn, chainn = runner.launch(3, "cuda-shared", parts, str(tmp_path), port=29691, **args)
+    whole = numpy.concatenate(parts)
+    pc = cw.cwipc_from_numpy_array(whole, 7)
+    ds = cw.cwipc_downsample(pc, 0.02)
+    assert len(dsn[1]) == 0 and len(sorn[1]) == 0
+    assert numpy.array_equal(sorted_records(numpy.concatenate(dsn)), sorted_records(ds.get_numpy_array()))
+    single = cw.cwipc_remove_outliers(pc, 10, 1.0, False)
+    assert abs(single.count() - sum(len(p) for p in sorn)) <= 2
+
+
 def test_slabs_nccl_one_gpu_per_rank(cw, tmp_path):
     if cw.cuda_device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
