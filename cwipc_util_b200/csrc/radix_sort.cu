@@ -499,8 +499,7 @@ bool launch_cluster_sort(const uint64_t *in, uint64_t *out, size_t n, int begin_
     if (ok[dev & 63] != 1) return false;
     const size_t cap = (size_t)RC_THREADS * IPT;
     const unsigned nctas = (unsigned)div_up(n, cap);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nctas);
     cfg.blockDim = dim3(RC_THREADS);
     cfg.dynamicSmemBytes = rc_smem_bytes<IPT>();
@@ -550,15 +549,13 @@ uint64_t *radix_sort_u64(uint64_t *a, uint64_t *b, size_t n, int begin_bit, int 
     // by the shared-memory pipe of each SM (match/LDS/STS per key), so the keys are spread over all 8 CTAs: the
     // smallest per-thread count that fits
     const size_t per_ipt = (size_t)RC_MAX_CTAS * RC_THREADS;
-    bool done = false, tried = true;
+    bool done = false;
     if (n <= per_ipt * 2) done = launch_cluster_sort<2>(a, b, n, begin_bit, end_bit, dev, s);
     else if (n <= per_ipt * 4) done = launch_cluster_sort<4>(a, b, n, begin_bit, end_bit, dev, s);
     else if (n <= per_ipt * 8) done = launch_cluster_sort<8>(a, b, n, begin_bit, end_bit, dev, s);
     else if (n <= per_ipt * 12) done = launch_cluster_sort<12>(a, b, n, begin_bit, end_bit, dev, s);
     else if (n <= per_ipt * 16) done = launch_cluster_sort<16>(a, b, n, begin_bit, end_bit, dev, s);
     else if (n <= per_ipt * 24) done = launch_cluster_sort<24>(a, b, n, begin_bit, end_bit, dev, s);
-    else tried = false;
-    (void)tried;
     if (done) return b;
     if ((int)ntiles <= fused_tile_limit(dev)) {
         const int fpasses = fused_passes(end_bit - begin_bit);
