@@ -32,6 +32,9 @@ import time
 
 import numpy as np
 
+# 15 streams per GPU: more hardware queues than the default 8 (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
