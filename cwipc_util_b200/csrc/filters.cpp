@@ -350,6 +350,7 @@ struct cwipc_cuda_distances {
     size_t n = 0;          // queries
     Scratch *mean = nullptr;   // float[n], owned (plain cudaMallocAsync blocks: they outlive the call that made them)
     Scratch *open_idx = nullptr; // uint32[nopen]
+    Scratch *kth = nullptr;      // float[n]: (k+1)-th smallest squared distance found so far (+inf where fewer points were seen)
     size_t nopen = 0;
 };
 
@@ -379,20 +380,24 @@ cwipc_cuda_distances *cwipc_cuda_knn_query_open(cwipc_pointcloud *pc, int kNeigh
         in->acquire_for_read(s);
         h->mean = persistent_scratch((size_t)nquery * sizeof(float), s);
         h->open_idx = persistent_scratch((size_t)nquery * sizeof(uint32_t), s);
+        h->kth = persistent_scratch((size_t)nquery * sizeof(float), s);
         try {
             if (in->count > (size_t)kNeighbors) {
                 Scratch d(in->count * sizeof(float), s), kth(in->count * sizeof(float), s);
                 float box[6];
                 knn_mean_distances(in->d_pts, in->count, kNeighbors, pc->cellsize(), bounds_of(*in, box), d.as<float>(), in->dev, s, kth.as<float>(), (size_t)nquery);
                 CWCU_CHECK(cudaMemcpyAsync(h->mean->p, d.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                CWCU_CHECK(cudaMemcpyAsync(h->kth->p, kth.p, (size_t)nquery * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 h->nopen = mark_open_queries(in->d_pts, kth.as<float>(), (size_t)nquery, x_lo, x_hi, h->open_idx->as<uint32_t>(), in->dev, s);
-            } else { // fewer points than neighbours here: every query is open
+            } else { // fewer points than neighbours here: every query is open, nothing is known about its neighbourhood
+                CWCU_CHECK(cudaMemsetAsync(h->kth->p, 0x7f, (size_t)nquery * sizeof(float), s)); // 0x7f7f7f7f: a huge finite float
                 h->nopen = mark_open_queries(in->d_pts, nullptr, (size_t)nquery, x_lo, x_hi, h->open_idx->as<uint32_t>(), in->dev, s);
             }
         } catch (...) {
             in->release_after_read(s);
             delete h->mean;
             delete h->open_idx;
+            delete h->kth;
             delete h;
             throw;
         }
@@ -402,8 +407,8 @@ cwipc_cuda_distances *cwipc_cuda_knn_query_open(cwipc_pointcloud *pc, int kNeigh
     });
 }
 
-// indices (into the first nquery points) and coordinates of the open queries, to host
-int cwipc_cuda_distances_open(cwipc_cuda_distances *h, cwipc_pointcloud *pc, uint32_t *idx, struct cwipc_point *points) {
+// indices (into the first nquery points), coordinates and current (k+1)-th squared distances of the open queries, to host
+int cwipc_cuda_distances_open(cwipc_cuda_distances *h, cwipc_pointcloud *pc, uint32_t *idx, struct cwipc_point *points, float *kth2) {
     if (h == nullptr || pc == nullptr) return -1;
     return guarded<int>("cwipc_cuda_distances_open", -1, [&]() -> int {
         if (h->nopen == 0) return 0;
@@ -416,6 +421,11 @@ int cwipc_cuda_distances_open(cwipc_cuda_distances *h, cwipc_pointcloud *pc, uin
         gather_points(in->d_pts, h->open_idx->as<uint32_t>(), h->nopen, q.as<cwipc_point>(), s);
         if (idx) CWCU_CHECK(cudaMemcpyAsync(idx, h->open_idx->p, h->nopen * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (points) CWCU_CHECK(cudaMemcpyAsync(points, q.p, h->nopen * sizeof(cwipc_point), cudaMemcpyDeviceToHost, s));
+        Scratch kq(h->nopen * sizeof(float), s);
+        if (kth2) {
+            gather_floats(h->kth->as<float>(), h->open_idx->as<uint32_t>(), h->nopen, kq.as<float>(), s);
+            CWCU_CHECK(cudaMemcpyAsync(kth2, kq.p, h->nopen * sizeof(float), cudaMemcpyDeviceToHost, s));
+        }
         in->release_after_read(s);
         stream_sync(s);
         return (int)h->nopen;
@@ -464,12 +474,13 @@ void cwipc_cuda_distances_free(cwipc_cuda_distances *h) {
         DeviceGuard g(h->dev);
         delete h->mean;
         delete h->open_idx;
+        delete h->kth;
     } catch (...) {
     }
     delete h;
 }
 
-int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, int nq, int kNeighbors, float *lists) {
+int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, const float *limits, int nq, int kNeighbors, float *lists) {
     if (pc == nullptr || nq < 0 || (nq > 0 && (queries == nullptr || lists == nullptr))) return -1;
     return guarded<int>("cwipc_cuda_knn_lists", -1, [&]() -> int {
         StoragePtr in = storage_of(pc, "cwipc_cuda_knn_lists");
@@ -479,10 +490,11 @@ int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries
         cudaStream_t s = thread_stream(in->dev);
         in->acquire_for_read(s);
         const size_t kk = (size_t)kNeighbors + 1;
-        Scratch q((size_t)nq * sizeof(cwipc_point), s), l((size_t)nq * kk * sizeof(float), s);
+        Scratch q((size_t)nq * sizeof(cwipc_point), s), l((size_t)nq * kk * sizeof(float), s), lim(limits ? (size_t)nq * sizeof(float) : 0, s);
         CWCU_CHECK(cudaMemcpyAsync(q.p, queries, (size_t)nq * sizeof(cwipc_point), cudaMemcpyHostToDevice, s));
+        if (limits) CWCU_CHECK(cudaMemcpyAsync(lim.p, limits, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, s));
         float box[6];
-        knn_lists(in->d_pts, in->count, q.as<cwipc_point>(), (size_t)nq, kNeighbors, pc->cellsize(), bounds_of(*in, box), l.as<float>(), in->dev, s);
+        knn_lists(in->d_pts, in->count, q.as<cwipc_point>(), limits ? lim.as<float>() : nullptr, (size_t)nq, kNeighbors, pc->cellsize(), bounds_of(*in, box), l.as<float>(), in->dev, s);
         CWCU_CHECK(cudaMemcpyAsync(lists, l.p, (size_t)nq * kk * sizeof(float), cudaMemcpyDeviceToHost, s));
         in->release_after_read(s);
         stream_sync(s);

@@ -62,7 +62,10 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
 void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s, float *d_kth = nullptr,
                         size_t nquery = (size_t)-1);
 // The k+1 smallest squared distances (ascending, +inf padded) from each of nq device-resident query points to the cloud.
-void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev, cudaStream_t s);
+// d_limits (nullable): per query, only distances <= limit are reported (a bound on its (k+1)-th distance found elsewhere)
+void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, const float *d_limits, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev,
+               cudaStream_t s);
+void gather_floats(const float *values, const uint32_t *idx, size_t n, float *out, cudaStream_t s);
 // lists laid out [nlists][nq][k+1]; mean distance to the k nearest (and k-th squared distance) of the merged lists
 void knn_merge_lists(const float *d_lists, size_t nlists, size_t nq, int k, float *d_mean, float *d_kth, cudaStream_t s);
 // sum d, sum (float)(d*d), both in double (synchronises the stream)

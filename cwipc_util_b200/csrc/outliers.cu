@@ -615,14 +615,15 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
 // Used when a cloud is partitioned over several GPUs: every part answers, the owner merges the lists.
 template <int KPL>
 __global__ void __launch_bounds__(KF_THREADS) knn_list_kernel(const cwipc_point *__restrict__ spts, uint32_t n, GridParams gp, int kk, const uint2 *__restrict__ table,
-                                                               const cwipc_point *__restrict__ queries, uint32_t nq, float *__restrict__ lists, uint32_t leaf_points) {
+                                                               const cwipc_point *__restrict__ queries, const float *__restrict__ limits, uint32_t nq, float *__restrict__ lists,
+                                                               uint32_t leaf_points) {
     __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
     for (uint32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < nq; qi += warps_total) {
         float v[KPL];
-        dfs_knn<KPL>(ld_point(queries, qi), INFINITY, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v);
+        dfs_knn<KPL>(ld_point(queries, qi), limits ? limits[qi] : INFINITY, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v);
 #pragma unroll
         for (int j = 0; j < KPL; j++) {
             const int e = j * 32 + (int)lane;
@@ -909,7 +910,8 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     else go(std::integral_constant<int, 64>{});
 }
 
-void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev, cudaStream_t s) {
+void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, const float *d_limits, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev,
+               cudaStream_t s) {
     check_k(k, n);
     if (nq == 0) return;
     const int kk = k + 1;
@@ -924,9 +926,9 @@ void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, si
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nq, (size_t)KF_WARPS), (size_t)sm_count(dev) * 8));
     launch("knn_list_kernel", s, (size_t)0, [&] {
         if (kk <= 32)
-            knn_list_kernel<1><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, (uint32_t)nq, d_lists, far_leaf_points());
+            knn_list_kernel<1><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, d_limits, (uint32_t)nq, d_lists, far_leaf_points());
         else
-            knn_list_kernel<2><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, (uint32_t)nq, d_lists, far_leaf_points());
+            knn_list_kernel<2><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, d_limits, (uint32_t)nq, d_lists, far_leaf_points());
     });
 }
 
@@ -977,6 +979,10 @@ __global__ void __launch_bounds__(256) gather_points_kernel(const cwipc_point *_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st_point(out, i, ld_point(pts, idx[i]));
 }
+__global__ void __launch_bounds__(256) gather_floats_kernel(const float *__restrict__ values, const uint32_t *__restrict__ idx, uint32_t n, float *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = values[idx[i]];
+}
 __global__ void __launch_bounds__(256) scatter_floats_kernel(const float *__restrict__ values, const uint32_t *__restrict__ idx, uint32_t n, float *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[idx[i]] = values[i];
@@ -1000,6 +1006,11 @@ size_t mark_open_queries(const cwipc_point *pts, const float *kth2, size_t nquer
 void gather_points(const cwipc_point *pts, const uint32_t *idx, size_t n, cwipc_point *out, cudaStream_t s) {
     if (n == 0) return;
     launch("gather_points_kernel", s, 36 * n, [&] { gather_points_kernel<<<(unsigned)div_up(n, 256), 256, 0, s>>>(pts, idx, (uint32_t)n, out); });
+}
+
+void gather_floats(const float *values, const uint32_t *idx, size_t n, float *out, cudaStream_t s) {
+    if (n == 0) return;
+    launch("gather_floats_kernel", s, 12 * n, [&] { gather_floats_kernel<<<(unsigned)div_up(n, 256), 256, 0, s>>>(values, idx, (uint32_t)n, out); });
 }
 
 void scatter_floats(const float *values, const uint32_t *idx, size_t n, float *out, cudaStream_t s) {

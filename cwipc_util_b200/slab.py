@@ -20,8 +20,9 @@ slab_remove_outliers (whole cloud, perTile=False)
   1. halo: every rank receives the points within H of its x-extent from the other ranks.
   2. kNN statistics of the local points against local+halo; a query is final when its (k+1)-th distance
      stays inside the covered interval.
-  3. the few queries that are not final (isolated points) are all-gathered; every rank answers with the k+1
-     smallest distances among its OWN points, the owner merges the lists: exact whatever H was.
+  3. the few queries that are not final (isolated points) are all-gathered with their current (k+1)-th distance;
+     every rank whose x-extent that distance reaches answers with the k+1 smallest distances among its OWN points,
+     the owner merges the lists: exact whatever H was.
   4. sum d, sum d*d, n are all-reduced; every rank thresholds its own points.
 """
 from __future__ import annotations
@@ -166,14 +167,14 @@ class CudaOps:
     def knn_open(self, pc, k: int, nquery: int, x_lo: float, x_hi: float):
         """Distances of the first nquery points of `pc` (kept on the device) + indices and coordinates of the open queries."""
         d = self.u.cuda_distances(pc, k, nquery, x_lo, x_hi)
-        idx, pts = d.open_queries()
-        return d, idx, pts
+        idx, pts, kth2 = d.open_queries()
+        return d, idx, pts, kth2
 
     def keep_all(self, pc):
         return self.u.cwipc_tilefilter(pc, 0)
 
-    def knn_lists(self, pc, queries: numpy.ndarray, k: int) -> numpy.ndarray:
-        return self.u.knn_lists(pc, queries, k)
+    def knn_lists(self, pc, queries: numpy.ndarray, k: int, limits: numpy.ndarray) -> numpy.ndarray:
+        return self.u.knn_lists(pc, queries, k, limits)
 
     def merge_lists(self, lists: numpy.ndarray, k: int) -> numpy.ndarray:
         return self.u.knn_merge_lists(lists, k)[0]
@@ -337,14 +338,24 @@ def slab_remove_outliers(pc, k: int, mul: float, comm: TorchComm, ops, halo: Opt
     others = [q for q in range(G) if q != r and counts[q] > 0]
     lo_lim = ext[r, 0] - H if any(ext[q, 0] < ext[r, 0] - H for q in others) else -numpy.inf
     hi_lim = ext[r, 1] + H if any(ext[q, 1] > ext[r, 1] + H for q in others) else numpy.inf
-    dists, open_idx, open_pts = ops.knn_open(combined, k, n_local, float(lo_lim), float(hi_lim))
+    dists, open_idx, open_pts, open_kth2 = ops.knn_open(combined, k, n_local, float(lo_lim), float(hi_lim))
 
-    # 3. the open queries: every rank answers from its own points, the owner merges
-    all_q = comm.allgather_bytes(open_pts)
+    # 3. the open queries: a rank answers, from its own points, those whose current (k+1)-th distance (an upper bound of
+    #    the final one) reaches its x-extent; the owner merges the lists
+    rec = numpy.zeros(len(open_pts), numpy.dtype([("p", open_pts.dtype), ("b", "<f4")]))
+    rec["p"], rec["b"] = open_pts, open_kth2
+    all_q = comm.allgather_bytes(rec)
     nq = [len(a) for a in all_q]
     if sum(nq):
         queries = numpy.concatenate(all_q)
-        lists = ops.knn_lists(pc, queries, k) if n_local else numpy.full((len(queries), k + 1), numpy.inf, numpy.float32)
+        lists = numpy.full((len(queries), k + 1), numpy.inf, numpy.float32)
+        if n_local:
+            qx = queries["p"]["x"].astype(numpy.float64)
+            rk = numpy.sqrt(queries["b"].astype(numpy.float64)) * (1.0 + 1e-6)
+            mine_too = (qx + rk >= ext[r, 0]) & (qx - rk <= ext[r, 1])
+            sel = numpy.nonzero(mine_too)[0]
+            if len(sel):
+                lists[sel] = ops.knn_lists(pc, numpy.ascontiguousarray(queries["p"][sel]), k, numpy.ascontiguousarray(queries["b"][sel]))
         all_lists = comm.allgather_bytes(lists)  # one [Q, k+1] block per rank
         if nq[r]:
             off = sum(nq[:r])

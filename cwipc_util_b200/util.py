@@ -154,13 +154,13 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
         "cwipc_cuda_downsample_planned": ([cwipc_pointcloud_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p], cwipc_pointcloud_p),
         "cwipc_cuda_from_device_points": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong], cwipc_pointcloud_p),
         "cwipc_cuda_knn_query": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
-        "cwipc_cuda_knn_lists": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_knn_lists": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_knn_merge_lists": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_distance_stats": ([ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_outlier_threshold": ([ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_float], ctypes.c_double),
         "cwipc_cuda_filter_by_distance": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double], cwipc_pointcloud_p),
         "cwipc_cuda_knn_query_open": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_void_p], ctypes.c_void_p),
-        "cwipc_cuda_distances_open": ([ctypes.c_void_p, cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_distances_open": ([ctypes.c_void_p, cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_distances_patch": ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int], ctypes.c_int),
         "cwipc_cuda_distances_stats": ([ctypes.c_void_p, ctypes.c_void_p], ctypes.c_int),
         "cwipc_cuda_distances_filter": ([cwipc_pointcloud_p, ctypes.c_void_p, ctypes.c_double], cwipc_pointcloud_p),
@@ -550,10 +550,11 @@ def knn_query(pc: cwipc_pointcloud_wrapper, kNeighbors: int, nquery: int):
     return mean, kth2
 
 
-def knn_lists(pc: cwipc_pointcloud_wrapper, queries: numpy.ndarray, kNeighbors: int) -> numpy.ndarray:
+def knn_lists(pc: cwipc_pointcloud_wrapper, queries: numpy.ndarray, kNeighbors: int, limits: Optional[numpy.ndarray] = None) -> numpy.ndarray:
     q = numpy.ascontiguousarray(queries)
     out = numpy.zeros((len(q), kNeighbors + 1), numpy.float32)
-    rv = cwipc_util_dll_load().cwipc_cuda_knn_lists(pc.as_cwipc_p(), q.ctypes.data, len(q), kNeighbors, out.ctypes.data)
+    lim = None if limits is None else numpy.ascontiguousarray(limits, numpy.float32)
+    rv = cwipc_util_dll_load().cwipc_cuda_knn_lists(pc.as_cwipc_p(), q.ctypes.data, None if lim is None else lim.ctypes.data, len(q), kNeighbors, out.ctypes.data)
     if rv < 0:
         raise CwipcError("cwipc_cuda_knn_lists failed")
     return out
@@ -621,9 +622,10 @@ class cuda_distances:
     def open_queries(self):
         idx = numpy.zeros(self.nopen, numpy.uint32)
         pts = numpy.zeros(self.nopen, cwipc_point_numpy_dtype)
-        if self.nopen and cwipc_util_dll_load().cwipc_cuda_distances_open(self._h, self._pc.as_cwipc_p(), idx.ctypes.data, pts.ctypes.data) < 0:
+        kth2 = numpy.zeros(self.nopen, numpy.float32)
+        if self.nopen and cwipc_util_dll_load().cwipc_cuda_distances_open(self._h, self._pc.as_cwipc_p(), idx.ctypes.data, pts.ctypes.data, kth2.ctypes.data) < 0:
             raise CwipcError("cwipc_cuda_distances_open failed")
-        return idx, pts
+        return idx, pts, kth2
 
     def patch(self, values: numpy.ndarray) -> None:
         v = numpy.ascontiguousarray(values, numpy.float32)

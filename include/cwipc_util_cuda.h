@@ -339,15 +339,17 @@ _CWIPC_UTIL_EXPORT int cwipc_cuda_knn_query(cwipc_pointcloud *pc, int kNeighbors
  * this part and therefore have to be completed with the other parts' points.  Only the open queries ever reach the host. */
 typedef struct cwipc_cuda_distances cwipc_cuda_distances;
 _CWIPC_UTIL_EXPORT cwipc_cuda_distances *cwipc_cuda_knn_query_open(cwipc_pointcloud *pc, int kNeighbors, int nquery, float x_lo, float x_hi, int *nopen);
-/* indices and coordinates of the open queries (nopen entries each, either may be NULL) */
-_CWIPC_UTIL_EXPORT int cwipc_cuda_distances_open(cwipc_cuda_distances *d, cwipc_pointcloud *pc, uint32_t *idx, struct cwipc_point *points);
+/* indices, coordinates and current (k+1)-th squared distances of the open queries (nopen entries each, any may be NULL);
+ * the distance is an upper bound of the final one: only parts within its reach have to answer the query */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_distances_open(cwipc_cuda_distances *d, cwipc_pointcloud *pc, uint32_t *idx, struct cwipc_point *points, float *kth2);
 /* overwrite the mean distance of the open queries, in the order cwipc_cuda_distances_open listed them */
 _CWIPC_UTIL_EXPORT int cwipc_cuda_distances_patch(cwipc_cuda_distances *d, const float *values, int n);
 _CWIPC_UTIL_EXPORT int cwipc_cuda_distances_stats(cwipc_cuda_distances *d, double sums[2]);
 _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_distances_filter(cwipc_pointcloud *pc, cwipc_cuda_distances *d, double threshold);
 _CWIPC_UTIL_EXPORT void cwipc_cuda_distances_free(cwipc_cuda_distances *d);
-/* The k+1 smallest squared distances (ascending, +inf padded) from nq arbitrary query points to the cloud: lists[nq][k+1]. */
-_CWIPC_UTIL_EXPORT int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, int nq, int kNeighbors, float *lists);
+/* The k+1 smallest squared distances (ascending, +inf padded) from nq arbitrary query points to the cloud: lists[nq][k+1].
+ * limits (may be NULL): per query, only distances <= limit are searched for and reported. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_knn_lists(cwipc_pointcloud *pc, const struct cwipc_point *queries, const float *limits, int nq, int kNeighbors, float *lists);
 /* Merge lists[nlists][nq][k+1] (one list per part of the cloud) into the mean distance / (k+1)-th squared distance. */
 _CWIPC_UTIL_EXPORT int cwipc_cuda_knn_merge_lists(const float *lists, int nlists, int nq, int kNeighbors, float *mean, float *kth2);
 /* sums[0] = sum d, sums[1] = sum (float)(d*d), in double: the two numbers the parts all-reduce. */

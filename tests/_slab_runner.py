@@ -110,7 +110,7 @@ class NumpyOps:
         x = q["x"].astype(numpy.float64)
         rk = numpy.sqrt(kth2.astype(numpy.float64)) * (1.0 + 1e-6)
         open_idx = numpy.nonzero(~((x - rk > x_lo) & (x + rk < x_hi)))[0].astype(numpy.uint32)
-        return {"mean": mean.copy(), "idx": open_idx}, open_idx, q[open_idx]
+        return {"mean": mean.copy(), "idx": open_idx}, open_idx, q[open_idx], numpy.minimum(kth2[open_idx], numpy.float32(3.0e38))
 
     def keep_all(self, pc):
         return pc
@@ -118,8 +118,10 @@ class NumpyOps:
     def patch(self, d, values):
         d["mean"][d["idx"]] = values
 
-    def knn_lists(self, pc, queries, k):
-        return _lists(queries, pc.pts, k)
+    def knn_lists(self, pc, queries, k, limits):
+        l = _lists(queries, pc.pts, k)
+        l[l > limits[:, None]] = numpy.inf   # only distances within the query's current bound are reported
+        return l
 
     def merge_lists(self, lists, k):
         merged = numpy.sort(numpy.concatenate(list(lists), axis=1), axis=1)[:, :k + 1]
