@@ -96,6 +96,13 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
     if _dll is not None:
         return _dll
     path = libname or os.environ.get("CWIPC_CUDA_LIBRARY") or _default_library_path()
+    if not os.path.exists(path) and not libname and not os.environ.get("CWIPC_CUDA_LIBRARY"):
+        # a fresh checkout (the .so is not in the history): build it in-tree with nvcc; this is still the CUDA library or nothing
+        try:
+            from . import build as _build
+            _build.build_library()
+        except Exception as e:  # pragma: no cover
+            raise RuntimeError(f"libcwipc_util_cuda not found at {path} and building it failed: {e}") from e
     if not os.path.exists(path):
         raise RuntimeError(f"libcwipc_util_cuda not found at {path}: build it with `python -m cwipc_util_b200.build` (there is no CPU fallback)")
     d = ctypes.CDLL(path)
