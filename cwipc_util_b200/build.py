@@ -9,6 +9,7 @@ built IN-TREE (cwipc_util_b200/lib/) so that the .so travels with the repo snaps
 from __future__ import annotations
 
 import concurrent.futures
+import fcntl
 import hashlib
 import os
 import shutil
@@ -79,13 +80,25 @@ def _is_current(stamp: str, digest: str, *artefacts: str) -> bool:
 
 def _compile_one(args) -> str:
     src, obj, verbose = args
-    cmd = [_nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", src, "-o", obj]
+    tmp = f"{obj}.tmp{os.getpid()}.o"
+    cmd = [_nvcc(), *NVCC_FLAGS, "-x", "cu", "-c", src, "-o", tmp]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, obj)   # never a half-written object under the final name
     return r.stderr if verbose else ""
+
+
+def _link(objs, target: str, soname: str) -> None:
+    tmp = f"{target}.tmp{os.getpid()}"
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-Xlinker", f"-soname={soname}", "-o", tmp, *objs, "-lpthread", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.chmod(tmp, 0o755)
+    os.replace(tmp, target)
 
 
 def lib_path() -> str:
@@ -93,6 +106,9 @@ def lib_path() -> str:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Build what is out of date.  Safe to call from several processes at once (every rank of a torchrun launch on a
+    fresh checkout does): the whole build runs under an exclusive file lock, the stamp is re-checked once the lock is
+    held, and objects / libraries are written under temporary names and renamed into place."""
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     hdr = _headers_digest()
@@ -109,26 +125,34 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     lib_stamp = os.path.join(LIB_DIR, ".stamp")
     if not force and _is_current(lib_stamp, lib_h.hexdigest(), target, dropin):
         return target
-    jobs, objs = [], []
-    for name in SOURCES:
-        src = os.path.join(CSRC_DIR, name)
-        obj = os.path.join(OBJ_DIR, name + ".o")
-        objs.append(obj)
-        if force or not _is_current(obj + ".stamp", digests[name], obj):
-            jobs.append((src, obj, verbose))
-    if jobs:
-        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            for out in ex.map(_compile_one, jobs):
-                if out:
-                    print(out, file=sys.stderr)
-        for src, obj, _ in jobs:
-            open(obj + ".stamp", "w").write(digests[os.path.basename(src)])
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", target, *objs, "-lpthread"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    shutil.copyfile(target, dropin)
-    open(lib_stamp, "w").write(lib_h.hexdigest())
+    with open(os.path.join(LIB_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _is_current(lib_stamp, lib_h.hexdigest(), target, dropin):
+                return target   # another process built it while we waited
+            jobs, objs = [], []
+            for name in SOURCES:
+                src = os.path.join(CSRC_DIR, name)
+                obj = os.path.join(OBJ_DIR, name + ".o")
+                objs.append(obj)
+                if force or not _is_current(obj + ".stamp", digests[name], obj):
+                    jobs.append((src, obj, verbose))
+            if jobs:
+                with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+                    for out in ex.map(_compile_one, jobs):
+                        if out:
+                            print(out, file=sys.stderr)
+                for src, obj, _ in jobs:
+                    open(obj + ".stamp", "w").write(digests[os.path.basename(src)])
+            _link(objs, target, LIB_NAME)
+            # the drop-in carries its own SONAME: ctypes.util.find_library('cwipc_util') (python/cwipc/util.py:149-161)
+            # resolves a library on LD_LIBRARY_PATH through its SONAME
+            _link(objs, dropin, DROPIN_NAME)
+            tmp = lib_stamp + f".tmp{os.getpid()}"
+            open(tmp, "w").write(lib_h.hexdigest())
+            os.replace(tmp, lib_stamp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return target
 
 

@@ -41,7 +41,11 @@ cwipc_pointcloud *make_from_points(const char *who, const cwipc_point *points, s
         log(CWIPC_LOG_LEVEL_ERROR, who, "cannot load points (size error?)");
         return nullptr;
     }
-    return guarded<cwipc_pointcloud *>(who, nullptr, [&]() -> cwipc_pointcloud * { return DevicePointcloud::from_host(points, (size_t)npoint, timestamp, sync); });
+    return guarded<cwipc_pointcloud *>(who, nullptr, [&]() -> cwipc_pointcloud * {
+        DevicePointcloud *pc = DevicePointcloud::from_host(points, (size_t)npoint, timestamp, sync);
+        pc->set_exact_size(true); // the reference's cwipc_uncompressed_impl: copy_uncompressed(size != exact) is an error
+        return pc;
+    });
 }
 
 struct Timer {
@@ -335,6 +339,13 @@ void cwipc_cuda_flush_l2(void) {
         const int dev = current_device();
         DeviceGuard g(dev);
         flush_l2(dev, thread_stream(dev));
+        return 0;
+    });
+}
+
+int cwipc_cuda_trim(void) {
+    return guarded<int>("cwipc_cuda_trim", -1, [&] {
+        trim_device(current_device());
         return 0;
     });
 }

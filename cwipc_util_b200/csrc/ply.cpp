@@ -68,6 +68,13 @@ int field_of(const std::string &n) {
     return -1;
 }
 
+void assign_packed(cwipc_point &pt, uint32_t rgba) { // a<<24 | r<<16 | g<<8 | b  (include/cwipc_util/api_pcl.h:20-55)
+    pt.tile = (uint8_t)(rgba >> 24);
+    pt.r = (uint8_t)(rgba >> 16);
+    pt.g = (uint8_t)(rgba >> 8);
+    pt.b = (uint8_t)rgba;
+}
+
 void assign(cwipc_point &pt, int field, double v) {
     switch (field) {
     case 0: pt.x = (float)v; break;
@@ -77,14 +84,7 @@ void assign(cwipc_point &pt, int field, double v) {
     case 4: pt.g = (uint8_t)v; break;
     case 5: pt.b = (uint8_t)v; break;
     case 6: pt.tile = (uint8_t)v; break;
-    case 7: {
-        const uint32_t rgba = (uint32_t)v; // a<<24 | r<<16 | g<<8 | b
-        pt.tile = (uint8_t)(rgba >> 24);
-        pt.r = (uint8_t)(rgba >> 16);
-        pt.g = (uint8_t)(rgba >> 8);
-        pt.b = (uint8_t)rgba;
-        break;
-    }
+    case 7: assign_packed(pt, (uint32_t)v); break;
     default: break;
     }
 }
@@ -148,7 +148,15 @@ bool read_ply(const char *filename, std::vector<cwipc_point> &points, std::strin
         std::vector<uint8_t> row(stride ? stride : 1);
         for (size_t v = 0; v < nvertex && ok; v++) {
             if (fread(row.data(), 1, stride, fp) != stride) { ok = false; break; }
-            for (size_t i = 0; i < props.size(); i++) assign(points[v], fields[i], read_binary(row.data() + props[i].offset, props[i].type));
+            for (size_t i = 0; i < props.size(); i++) {
+                if (fields[i] == 7 && props[i].type == T_FLOAT32) { // legacy "float rgb": the float's bits are the packed word
+                    uint32_t bits;
+                    memcpy(&bits, row.data() + props[i].offset, 4);
+                    assign_packed(points[v], bits);
+                } else {
+                    assign(points[v], fields[i], read_binary(row.data() + props[i].offset, props[i].type));
+                }
+            }
         }
     } else {
         for (size_t k = 0; k < skip_before; k++)
@@ -161,7 +169,14 @@ bool read_ply(const char *filename, std::vector<cwipc_point> &points, std::strin
                 const double val = strtod(cur, &end);
                 if (end == cur) { ok = false; break; }
                 cur = end;
-                assign(points[v], fields[i], val);
+                if (fields[i] == 7 && props[i].type == T_FLOAT32) {
+                    const float f = (float)val;
+                    uint32_t bits;
+                    memcpy(&bits, &f, 4);
+                    assign_packed(points[v], bits);
+                } else {
+                    assign(points[v], fields[i], val);
+                }
             }
         }
     }

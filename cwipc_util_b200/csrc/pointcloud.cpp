@@ -78,7 +78,9 @@ void DevicePointcloud::free() {
 }
 
 cwipc_pointcloud *DevicePointcloud::_shallowcopy() {
-    return new DevicePointcloud(m_store, m_timestamp, m_cellsize);
+    auto *rv = new DevicePointcloud(m_store, m_timestamp, m_cellsize);
+    rv->m_exact_size = m_exact_size;
+    return rv;
 }
 
 void DevicePointcloud::_set_cellsize(float cellsize) {
@@ -120,7 +122,7 @@ int DevicePointcloud::copy_uncompressed(struct cwipc_point *pointbuf, size_t siz
         return 0;
     }
     const size_t need = m_store->count * sizeof(cwipc_point);
-    if (size < need) {
+    if (m_exact_size ? size != need : size < need) {
         log(CWIPC_LOG_LEVEL_ERROR, "cwipc_util", "copy_uncompressed: buffer too small");
         return -1;
     }

@@ -33,6 +33,10 @@ class DevicePointcloud : public cwipc_pointcloud {
     uint64_t m_timestamp = 0;
     float m_cellsize = 0.f;
     MetadataCollection *m_metadata = nullptr;
+    // Clouds made from a caller's point array (cwipc_from_points / cwipc_from_packet / read_debugdump) are the
+    // reference's cwipc_uncompressed_impl, whose copy_uncompressed wants the EXACT size (src/cwipc_util.cpp:393-397);
+    // filter results are its cwipc_impl, which accepts any buffer that is large enough (:226-231).
+    bool m_exact_size = false;
 
 public:
     DevicePointcloud(StoragePtr store, uint64_t timestamp, float cellsize);
@@ -42,6 +46,7 @@ public:
     static DevicePointcloud *from_host(const cwipc_point *points, size_t npoint, uint64_t timestamp, bool sync);
 
     const StoragePtr &storage() const { return m_store; }
+    void set_exact_size(bool on) { m_exact_size = on; }
 
     void free() override;
     cwipc_pointcloud *_shallowcopy() override;

@@ -28,6 +28,8 @@ struct DeviceState {
     std::vector<cudaStream_t> idle_streams; // streams returned by exited threads
     std::vector<std::pair<void *, size_t>> idle_zeroed; // workspaces returned by exited threads (contents unknown)
     std::vector<std::pair<char *, size_t>> idle_arena;  // scratch arena blocks returned by exited threads
+    std::vector<cudaEvent_t> idle_events;               // timing-disabled events; an event belongs to the device it was created on
+    cudaMemPool_t pool = nullptr;                       // the library's own stream-ordered pool on this device
 };
 
 int g_ndev = -1;
@@ -35,9 +37,9 @@ std::once_flag g_ndev_once;
 DeviceState *g_devs = nullptr;
 
 void init_devices() {
-    // One stream per caller thread: with the default of 8 hardware queues, 15 streams share queues and falsely
-    // serialise (measured +3.5 % frame throughput with 32).  Only effective if no CUDA context exists yet.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // The library does not touch process-wide CUDA settings.  A host that drives one GPU from more than 8 threads (one
+    // stream each) should export CUDA_DEVICE_MAX_CONNECTIONS=32 before the first CUDA call so that the streams do not
+    // share hardware queues (bench.py does; measured +3.5 % frame throughput).
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) {
@@ -55,11 +57,18 @@ void init_device(int dev) {
         cudaDeviceProp prop;
         CWCU_CHECK(cudaGetDeviceProperties(&prop, dev));
         st.sm_count = prop.multiProcessorCount;
-        // keep freed blocks cached in the pool: steady-state frames never hit cudaMalloc
-        cudaMemPool_t pool;
-        CWCU_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        // A private pool (the device's default pool, which the host application and other libraries may use, is left
+        // alone).  Freed blocks stay cached in it, so steady-state frames never reach cudaMalloc; cwipc_cuda_trim()
+        // hands the cache back to the driver.
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        CWCU_CHECK(cudaMemPoolCreate(&st.pool, &props));
         uint64_t threshold = UINT64_MAX;
-        CWCU_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        CWCU_CHECK(cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     });
 }
 
@@ -177,8 +186,11 @@ cudaStream_t thread_stream(int dev) {
 // ------------------------------------------------------------------------------------------
 void *dmalloc(size_t bytes, cudaStream_t s) {
     if (bytes == 0) bytes = 16;
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    init_device(dev);
     void *p = nullptr;
-    CWCU_CHECK(cudaMallocAsync(&p, bytes, s));
+    CWCU_CHECK(cudaMallocFromPoolAsync(&p, bytes, g_devs[dev].pool, s));
     return p;
 }
 
@@ -244,7 +256,7 @@ void scratch_free(void *p, cudaStream_t s, bool from_arena) noexcept {
         for (auto &b : a.blocks) dfree(b.first, s);
         a.blocks.clear();
         void *q = nullptr;
-        if (cudaMallocAsync(&q, cap, s) == cudaSuccess) a.blocks.emplace_back(static_cast<char *>(q), cap);
+        if (cudaMallocFromPoolAsync(&q, cap, g_devs[dev].pool, s) == cudaSuccess) a.blocks.emplace_back(static_cast<char *>(q), cap);
         else (void)cudaGetLastError();
     }
     a.offset = 0;
@@ -369,29 +381,58 @@ bool is_pinned_host(const void *p) {
 // ------------------------------------------------------------------------------------------
 // events
 // ------------------------------------------------------------------------------------------
-namespace {
-std::mutex g_event_mu;
-std::vector<cudaEvent_t> g_event_pool;
-} // namespace
-
-cudaEvent_t event_acquire() {
+// One pool per device: cudaEventRecord wants the event and the stream on the same device, so an event freed by a cloud on
+// device 0 must never be handed to a cloud on device 1 (one process, one thread per GPU: DESIGN.md section 7).
+cudaEvent_t event_acquire(int dev) {
+    init_device(dev);
+    DeviceState &st = g_devs[dev];
     {
-        std::lock_guard<std::mutex> lk(g_event_mu);
-        if (!g_event_pool.empty()) {
-            cudaEvent_t e = g_event_pool.back();
-            g_event_pool.pop_back();
+        std::lock_guard<std::mutex> lk(st.mu);
+        if (!st.idle_events.empty()) {
+            cudaEvent_t e = st.idle_events.back();
+            st.idle_events.pop_back();
             return e;
         }
     }
+    DeviceGuard g(dev);
     cudaEvent_t e;
     CWCU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return e;
 }
 
-void event_release(cudaEvent_t e) noexcept {
-    if (!e) return;
-    std::lock_guard<std::mutex> lk(g_event_mu);
-    g_event_pool.push_back(e);
+void event_release(int dev, cudaEvent_t e) noexcept {
+    if (!e || !g_devs || dev < 0 || dev >= g_ndev) return;
+    std::lock_guard<std::mutex> lk(g_devs[dev].mu);
+    g_devs[dev].idle_events.push_back(e);
+}
+
+// Hand cached memory back to the driver: idle arenas / workspaces of exited threads, the calling thread's own arena and
+// zeroed workspace on `dev`, and everything the pool holds beyond what is in use.
+void trim_device(int dev) {
+    if (dev < 0 || dev >= device_count()) return;
+    init_device(dev);
+    DeviceGuard g(dev);
+    DeviceState &st = g_devs[dev];
+    CWCU_CHECK(cudaDeviceSynchronize());
+    std::vector<void *> drop;
+    {
+        std::lock_guard<std::mutex> lk(st.mu);
+        for (auto &b : st.idle_arena) drop.push_back(b.first);
+        for (auto &z : st.idle_zeroed) drop.push_back(z.first);
+        st.idle_arena.clear();
+        st.idle_zeroed.clear();
+    }
+    if ((int)t_state.arenas.size() > dev && t_state.arenas[dev].live == 0) {
+        for (auto &b : t_state.arenas[dev].blocks) drop.push_back(b.first);
+        t_state.arenas[dev].blocks.clear();
+        t_state.arenas[dev].offset = t_state.arenas[dev].used = 0;
+    }
+    if ((int)t_state.zeroed.size() > dev && t_state.zeroed[dev].p) {
+        drop.push_back(t_state.zeroed[dev].p);
+        t_state.zeroed[dev] = ThreadState::Zeroed();
+    }
+    for (void *p : drop) CWCU_CHECK(cudaFree(p));
+    CWCU_CHECK(cudaMemPoolTrimTo(st.pool, 0));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -400,7 +441,7 @@ void event_release(cudaEvent_t e) noexcept {
 Storage::Storage(int dev_, size_t capacity_, cudaStream_t home_) : dev(dev_), capacity(capacity_), home(home_) {
     DeviceGuard g(dev);
     d_pts = capacity ? static_cast<cwipc_point *>(dmalloc(capacity * sizeof(cwipc_point), home)) : nullptr;
-    ready = event_acquire();
+    ready = event_acquire(dev);
 }
 
 Storage::~Storage() {
@@ -408,11 +449,11 @@ Storage::~Storage() {
     try {
         DeviceGuard g(dev);
         for (auto &r : readers) {
-            (void)cudaStreamWaitEvent(home, r.second, 0);
-            event_release(r.second);
+            (void)cudaStreamWaitEvent(home, r.event, 0);
+            event_release(r.dev, r.event);
         }
         dfree(d_pts, home);
-        event_release(ready);
+        event_release(dev, ready);
     } catch (...) {
     }
 }
@@ -427,14 +468,17 @@ void Storage::release_after_read(cudaStream_t s) {
     if (s == home) return;
     std::lock_guard<std::mutex> lk(mu);
     for (auto &r : readers) {
-        if (r.first == s) {
-            CWCU_CHECK(cudaEventRecord(r.second, s));
+        if (r.stream == s) {
+            CWCU_CHECK(cudaEventRecord(r.event, s));
             return;
         }
     }
-    cudaEvent_t e = event_acquire();
+    // `s` is a stream of the CUDA-current device (the caller holds a DeviceGuard for it), which need not be this->dev
+    int sdev = 0;
+    CWCU_CHECK(cudaGetDevice(&sdev));
+    cudaEvent_t e = event_acquire(sdev);
     CWCU_CHECK(cudaEventRecord(e, s));
-    readers.emplace_back(s, e);
+    readers.push_back(Reader{s, e, sdev});
 }
 
 // ------------------------------------------------------------------------------------------

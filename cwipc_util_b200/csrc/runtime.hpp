@@ -6,8 +6,8 @@
 //    ("home") and an event recorded when its contents became valid.  A consumer on another
 //    stream waits on that event; the storage is returned to the pool on its home stream after
 //    waiting for every foreign reader.  No global lock is held while work is queued.
-//  * device memory comes from the device's default cudaMemPool (cudaMallocAsync) with the release
-//    threshold raised, so steady-state frames never reach cudaMalloc.
+//  * device memory comes from a private cudaMemPool per device (cudaMallocFromPoolAsync) with the release
+//    threshold raised, so steady-state frames never reach cudaMalloc; the device's default pool is not touched.
 //  * there is NO host fallback: every entry point that needs a device fails loudly without one.
 #pragma once
 
@@ -111,8 +111,9 @@ struct Scratch {
 void stream_sync(cudaStream_t s);
 
 // ---- events ----
-cudaEvent_t event_acquire();             // timing disabled
-void event_release(cudaEvent_t e) noexcept;
+cudaEvent_t event_acquire(int dev);      // timing disabled; created on (and only ever reused on) `dev`
+void event_release(int dev, cudaEvent_t e) noexcept;
+void trim_device(int dev);               // release cached device memory (see cwipc_cuda_trim)
 
 // ---- point storage ----
 // `count` valid 16-byte points at d_pts (capacity >= count).  Immutable once `ready` has fired.
@@ -124,7 +125,12 @@ struct Storage {
     cudaStream_t home = nullptr;
     cudaEvent_t ready = nullptr;
     std::mutex mu;
-    std::vector<std::pair<cudaStream_t, cudaEvent_t>> readers; // latest read per foreign stream
+    struct Reader {
+        cudaStream_t stream;
+        cudaEvent_t event;
+        int dev; // device of `stream` (and of `event`)
+    };
+    std::vector<Reader> readers; // latest read per foreign stream
     // A box known to contain every point (not necessarily tight), when a producer had one for free.
     bool has_bounds = false;
     float bounds_min[3] = {0, 0, 0}, bounds_max[3] = {0, 0, 0};

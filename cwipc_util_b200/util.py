@@ -184,6 +184,7 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
         "cwipc_cuda_profile_reset": ([], None),
         "cwipc_cuda_profile_report": ([ctypes.c_char_p, ctypes.c_size_t], ctypes.c_size_t),
         "cwipc_cuda_flush_l2": ([], None),
+        "cwipc_cuda_trim": ([], ctypes.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(d, name)

@@ -382,6 +382,10 @@ _CWIPC_UTIL_EXPORT void cwipc_cuda_profile_reset(void);
 _CWIPC_UTIL_EXPORT size_t cwipc_cuda_profile_report(char *buf, size_t size);
 /* Overwrite a buffer larger than L2 on the calling thread's stream (bench hygiene). */
 _CWIPC_UTIL_EXPORT void cwipc_cuda_flush_l2(void);
+/* Hand cached device memory of the calling thread's current device back to the driver (the library's private memory pool,
+ * the calling thread's scratch arena and voxel-table workspace, those of exited threads).  Waits for the device to go idle.
+ * Live clouds are not affected.  Returns 0, or -1 on error. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_trim(void);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,25 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* The two restatements that depend on the PCL release ("lowest-confidence items") are
+ * compile-time switches; the defaults are what the CUDA library implements and what the parity tests
+ * assert.  `make` also builds libcwipc_oracle_alt.so with both flipped, and tests/test_oracle.py checks
+ * what each switch may and may not change (see orc_config()).
+ *   ORC_LEAF_ORDER_DESCENDING  0: octree leaves are visited children 0..7 (PCL >= 1.9, DFS = ascending
+ *                                 Morton code); 1: children 7..0 (older releases) -- only the ORDER of the
+ *                                 per-leaf blocks in the output changes, never their contents.
+ *   ORC_VOXEL_SORT_UNSTABLE    0: points of one voxel are summed in input order (a stable sort);
+ *                              1: in reversed order (stands in for boost spreadsort / std::sort, whose
+ *                                 order among equal keys is unspecified) -- only the float rounding of the
+ *                                 centroid changes (inside the 1e-5 tolerance), colours/tiles/counts do not. */
+#ifndef ORC_LEAF_ORDER_DESCENDING
+#define ORC_LEAF_ORDER_DESCENDING 0
+#endif
+#ifndef ORC_VOXEL_SORT_UNSTABLE
+#define ORC_VOXEL_SORT_UNSTABLE 0
+#endif
+int orc_config(void) { return (ORC_LEAF_ORDER_DESCENDING ? 1 : 0) | (ORC_VOXEL_SORT_UNSTABLE ? 2 : 0); }
+
 /* ------------------------------------------------------------------------------------------ */
 /* helpers                                                                                      */
 /* ------------------------------------------------------------------------------------------ */
@@ -133,6 +152,18 @@ static long voxelgrid_subset(const orc_point *in, const uint32_t *subset, size_t
         int bits = bit_length64(cells - 1);
         sort_keyidx(kv, m, bits > 0 ? bits : 1);
     }
+#if ORC_VOXEL_SORT_UNSTABLE
+    for (size_t a = 0; a < m;) { /* reverse every run of equal keys */
+        size_t e = a + 1;
+        while (e < m && kv[e].key == kv[a].key) e++;
+        for (size_t lo = a, hi = e - 1; lo < hi; lo++, hi--) {
+            keyidx t = kv[lo];
+            kv[lo] = kv[hi];
+            kv[hi] = t;
+        }
+        a = e;
+    }
+#endif
     long nout = 0;
     size_t j = 0;
     while (j < m) {
@@ -256,6 +287,9 @@ long orc_downsample(const orc_point *in, size_t n, float voxelsize, float pc_cel
         uint32_t ly = (uint32_t)(((double)in[i].y - mn[1]) / res);
         uint32_t lz = (uint32_t)(((double)in[i].z - mn[2]) / res);
         kv[i].key = morton3(lx, ly, lz);
+#if ORC_LEAF_ORDER_DESCENDING
+        kv[i].key = (((uint64_t)1 << (3 * depth)) - 1) - kv[i].key; /* children visited 7..0 at every level */
+#endif
         kv[i].idx = (uint32_t)i;
         if (point_keys) {
             point_keys[6 * i + 0] = (int32_t)lx;

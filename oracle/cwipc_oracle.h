@@ -52,6 +52,10 @@ int orc_knn_mean_distances(const orc_point *in, size_t n, int k, float *mean_dis
  * threshold of the whole-cloud pass (perTile == 0 only). */
 long orc_remove_outliers(const orc_point *in, size_t n, int k, float stddev_mul, int per_tile, orc_point *out, double *threshold_out);
 
+/* bit 0: ORC_LEAF_ORDER_DESCENDING, bit 1: ORC_VOXEL_SORT_UNSTABLE (compile-time switches, see cwipc_oracle.c).
+ * The default build returns 0. */
+int orc_config(void);
+
 /* O(n^2) kNN used to pin the kd-tree on small inputs. */
 int orc_knn_mean_distances_bruteforce(const orc_point *in, size_t n, int k, float *mean_dist);
 

@@ -15,38 +15,52 @@ import numpy
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libcwipc_oracle.so")
+LIB_ALT = os.path.join(HERE, "libcwipc_oracle_alt.so")   # both PCL-release-dependent switches flipped (see cwipc_oracle.c)
 
 POINT_DTYPE = numpy.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1"), ("tile", "u1")])
 
 _lib: Optional[ctypes.CDLL] = None
+_lib_alt: Optional[ctypes.CDLL] = None
 
 
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "cwipc_oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "cwipc_oracle.h"))):
-        subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "cwipc_oracle.h")), os.path.getmtime(os.path.join(HERE, "Makefile")))
+    if force or any(not os.path.exists(l) or os.path.getmtime(l) < newest for l in (LIB, LIB_ALT)):
+        subprocess.run(["make", "-C", HERE, "-B", "all"], check=True, capture_output=True)
     return LIB
 
 
-def load() -> ctypes.CDLL:
-    global _lib
+def _declare(lib: ctypes.CDLL) -> ctypes.CDLL:
+    vp, sz = ctypes.c_void_p, ctypes.c_size_t
+    lib.orc_config.argtypes = []
+    lib.orc_config.restype = ctypes.c_int
+    lib.orc_tilefilter.argtypes = [vp, sz, ctypes.c_int, vp]
+    lib.orc_tilefilter.restype = ctypes.c_long
+    lib.orc_min_distance_to_first.argtypes = [vp, sz]
+    lib.orc_min_distance_to_first.restype = ctypes.c_float
+    lib.orc_downsample.argtypes = [vp, sz, ctypes.c_float, ctypes.c_float, vp, ctypes.POINTER(ctypes.c_float), vp, vp]
+    lib.orc_downsample.restype = ctypes.c_long
+    lib.orc_knn_mean_distances.argtypes = [vp, sz, ctypes.c_int, vp]
+    lib.orc_knn_mean_distances.restype = ctypes.c_int
+    lib.orc_knn_mean_distances_bruteforce.argtypes = [vp, sz, ctypes.c_int, vp]
+    lib.orc_knn_mean_distances_bruteforce.restype = ctypes.c_int
+    lib.orc_remove_outliers.argtypes = [vp, sz, ctypes.c_int, ctypes.c_float, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_double)]
+    lib.orc_remove_outliers.restype = ctypes.c_long
+    return lib
+
+
+def load(alt: bool = False) -> ctypes.CDLL:
+    """The default oracle, or (alt=True) the build with ORC_LEAF_ORDER_DESCENDING and ORC_VOXEL_SORT_UNSTABLE set."""
+    global _lib, _lib_alt
+    if alt:
+        if _lib_alt is None:
+            build()
+            _lib_alt = _declare(ctypes.CDLL(LIB_ALT))
+        return _lib_alt
     if _lib is None:
         build()
-        lib = ctypes.CDLL(LIB)
-        vp, sz = ctypes.c_void_p, ctypes.c_size_t
-        lib.orc_tilefilter.argtypes = [vp, sz, ctypes.c_int, vp]
-        lib.orc_tilefilter.restype = ctypes.c_long
-        lib.orc_min_distance_to_first.argtypes = [vp, sz]
-        lib.orc_min_distance_to_first.restype = ctypes.c_float
-        lib.orc_downsample.argtypes = [vp, sz, ctypes.c_float, ctypes.c_float, vp, ctypes.POINTER(ctypes.c_float), vp, vp]
-        lib.orc_downsample.restype = ctypes.c_long
-        lib.orc_knn_mean_distances.argtypes = [vp, sz, ctypes.c_int, vp]
-        lib.orc_knn_mean_distances.restype = ctypes.c_int
-        lib.orc_knn_mean_distances_bruteforce.argtypes = [vp, sz, ctypes.c_int, vp]
-        lib.orc_knn_mean_distances_bruteforce.restype = ctypes.c_int
-        lib.orc_remove_outliers.argtypes = [vp, sz, ctypes.c_int, ctypes.c_float, ctypes.c_int, vp, ctypes.POINTER(ctypes.c_double)]
-        lib.orc_remove_outliers.restype = ctypes.c_long
-        _lib = lib
+        _lib = _declare(ctypes.CDLL(LIB))
     return _lib
 
 
@@ -67,7 +81,7 @@ def min_distance_to_first(pts: numpy.ndarray) -> float:
     return float(load().orc_min_distance_to_first(pts.ctypes.data, len(pts)))
 
 
-def downsample(pts: numpy.ndarray, voxelsize: float, pc_cellsize: float = 0.0, want_keys: bool = False):
+def downsample(pts: numpy.ndarray, voxelsize: float, pc_cellsize: float = 0.0, want_keys: bool = False, alt: bool = False):
     """Returns (out_points or None, cellsize, point_keys (n,6) or None, counts)."""
     pts = _pts(pts)
     n = len(pts)
@@ -75,7 +89,7 @@ def downsample(pts: numpy.ndarray, voxelsize: float, pc_cellsize: float = 0.0, w
     counts = numpy.zeros(max(n, 1), numpy.uint32)
     keys = numpy.zeros((max(n, 1), 6), numpy.int32) if want_keys else None
     cs = ctypes.c_float(0)
-    m = load().orc_downsample(pts.ctypes.data, n, voxelsize, pc_cellsize, out.ctypes.data, ctypes.byref(cs), keys.ctypes.data if want_keys else None, counts.ctypes.data)
+    m = load(alt).orc_downsample(pts.ctypes.data, n, voxelsize, pc_cellsize, out.ctypes.data, ctypes.byref(cs), keys.ctypes.data if want_keys else None, counts.ctypes.data)
     if m < 0:
         return None, cs.value, (keys[:n] if want_keys else None), None
     return out[:m].copy(), cs.value, (keys[:n] if want_keys else None), counts[:m].copy()
