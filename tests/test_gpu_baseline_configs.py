@@ -16,7 +16,7 @@ import numpy as np
 import pytest
 
 from cwipc_util_b200 import synthetic
-from parity_helpers import assert_points_close, canonical_ranks, per_tile_check, sor_group_check
+from parity_helpers import assert_exact_means, assert_points_close, canonical_ranks, per_tile_check, sor_group_check
 
 pytestmark = pytest.mark.gpu
 
@@ -73,11 +73,13 @@ def test_config4_downsample_8m_octree_mode(cw, orc, cloud8m, voxel):
     assert out.cellsize() == np.float32(cs) == np.float32(voxel)
     got = download(out)
     assert len(got) == len(want)
-    assert_points_close(got, want, cs)
+    assert_points_close(got, want, cs, counts)
     gkeys = cw.util.downsample_keys(pc, voxel)
     _, inverse = np.unique(gkeys, return_inverse=True)
-    assert np.array_equal(inverse, canonical_ranks(keys6))
+    ranks = canonical_ranks(keys6)
+    assert np.array_equal(inverse, ranks)
     assert np.array_equal(np.bincount(inverse, minlength=len(want)), counts)
+    assert_exact_means(got, pts, ranks, counts, cs)
 
 
 def test_config4_chain_8m(cw, orc, cloud8m):
@@ -105,9 +107,11 @@ def test_config5_bench_frames(cw, orc, seed):
     o = cw.cwipc_remove_outliers(d, bench.K, bench.STDDEV, False)
     want, cs, keys6, counts = orc.downsample(frame, bench.VOXEL, cellsize, want_keys=True)
     gd = download(d)
-    assert_points_close(gd, want, cs)
+    assert_points_close(gd, want, cs, counts)
     _, inverse = np.unique(cw.util.downsample_keys(pc, bench.VOXEL), return_inverse=True)
-    assert np.array_equal(inverse, canonical_ranks(keys6))
+    ranks = canonical_ranks(keys6)
+    assert np.array_equal(inverse, ranks)
+    assert_exact_means(gd, frame, ranks, counts, cs)
     go = download(o)
     assert sor_group_check(gd, go, 0, orc.knn_mean_distances(gd, bench.K), bench.STDDEV) == len(go)
     assert o.cellsize() == np.float32(cs) and o.timestamp() == seed

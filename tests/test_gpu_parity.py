@@ -626,3 +626,49 @@ def test_two_devices_in_one_process(cw):
     b.free()
     a.free()
     assert cw.util.cwipc_util_dll_load().cwipc_cuda_trim() == 0
+
+
+@pytest.mark.parametrize("path", ["twopass", "generic", "smalltable"])
+def test_downsample_every_internal_path_matches_oracle(cw, orc, path):
+    """The fused single pass is the default; the two-pass path (leaf tables of the final octree box), the generic path
+    (double arithmetic per run, used when a cloud spans more than 32 leaves per axis) and the table-overflow retry are
+    forced here through CWIPC_CUDA_DS_PATH and must give the same results."""
+    clouds = [(synthetic.camera_cloud(250000, seed=3), 0.004, 0.0), (synthetic.synthetic_cloud(160000), 0.005, 0.005), (random_cloud(120000, seed=9, extent=0.4), 0.013, 0.0)]
+    os.environ["CWIPC_CUDA_DS_PATH"] = path
+    try:
+        for pts, voxel, pc_cellsize in clouds:
+            for v in (voxel, -voxel):
+                want, cs, keys6, counts = orc.downsample(pts, v, pc_cellsize, want_keys=True)
+                got = download(cw.cwipc_downsample(upload(cw, pts, cellsize=pc_cellsize), v))
+                assert_points_close(got, want, cs)
+    finally:
+        del os.environ["CWIPC_CUDA_DS_PATH"]
+
+
+def test_downsample_far_outlier_and_wide_clouds(cw, orc):
+    """One distant noise point on a fine grid (the octree grows deep, most points lie outside the leaf tables of the first
+    point), and a cloud more than 32 leaves wide: both stay correct (the sort word used to overflow here)."""
+    pts = synthetic.camera_cloud(100000, seed=21)
+    pts["x"][777], pts["y"][777], pts["z"][777] = 9.0, -7.5, 3.25
+    for voxel in (0.002, 0.004):
+        want, cs, _, _ = orc.downsample(pts, voxel, 0.0)
+        assert_points_close(download(cw.cwipc_downsample(upload(cw, pts), voxel)), want, cs)
+    wide = random_cloud(200000, seed=12, extent=3.0)
+    want, cs, _, _ = orc.downsample(wide, 0.002, 0.0)       # 6 m / (64 * 2 mm) = 47 leaves per axis
+    assert_points_close(download(cw.cwipc_downsample(upload(cw, wide), 0.002)), want, cs)
+
+
+def test_downsample_first_point_on_coordinate_planes(cw, orc):
+    """The octree is anchored on the first point: with p0 = (0, 0, z) leaf faces lie exactly on the planes x = 0 and y = 0,
+    where whole rings of the clean synthetic cloud sit, and floats next to zero vanish in (double)x - min.  Includes
+    denormal and 1e-20-sized coordinates, which the single-pass path must hand to the two-pass path."""
+    pts = synthetic.simulate_cameras(synthetic.synthetic_cloud(250000), 4)
+    for voxel in (0.005, 0.01, 0.05):
+        want, cs, _, counts = orc.downsample(pts, voxel, 0.0)
+        assert_points_close(download(cw.cwipc_downsample(upload(cw, pts), voxel)), want, cs)
+    tiny = pts.copy()
+    tiny["x"][1000:1010] = [1e-20, -1e-20, 1e-30, -1e-38, 1e-44, -1e-45, 3e-17, -3e-17, 1e-12, -1e-12]
+    tiny["y"][2000:2004] = [1e-20, 1e-41, -1e-20, 2e-17]
+    for voxel in (0.005, 0.02):
+        want, cs, _, counts = orc.downsample(tiny, voxel, 0.0)
+        assert_points_close(download(cw.cwipc_downsample(upload(cw, tiny), voxel)), want, cs)
