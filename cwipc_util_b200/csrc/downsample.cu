@@ -61,6 +61,7 @@ struct OctreeBox {
     int shift[3];
     int fallback; // 1: the relative keys cannot be trusted (rounding at a leaf face): redo with the two-pass path
     unsigned long long tail_ns; // diagnostics: time the last block spent on the replay and the checks
+    double m0[3];               // min corner of the first point's box: what the relative leaf indices count from
 };
 
 // ---- per-chunk bounding boxes --------------------------------------------------------------------------
@@ -360,6 +361,16 @@ __host__ __device__ __forceinline__ uint64_t spread3(uint32_t v) { // bit i -> b
     return x;
 }
 
+__host__ __device__ __forceinline__ uint32_t compact3(uint64_t x) { // inverse of spread3
+    x &= 0x1249249249249249ull;
+    x = (x | x >> 2) & 0x10c30c30c30c30c3ull;
+    x = (x | x >> 4) & 0x100f00f00f00f00full;
+    x = (x | x >> 8) & 0x1f0000ff0000ffull;
+    x = (x | x >> 16) & 0x1f00000000ffffull;
+    x = (x | x >> 32) & 0x1fffffull;
+    return (uint32_t)x;
+}
+
 // Leaf lookup tables (octree mode): the leaf index of a coordinate is a step function of the float32 value, so the
 // smallest float at which every step happens is found once, with the very double arithmetic of the generic path, and a
 // point then costs two or three float compares per axis instead of double-precision subtract / divide / floor.
@@ -527,6 +538,7 @@ constexpr int VS_TILE = 32 * VS_L;            // points per warp tile (= points 
 constexpr int VS_WARPS = 8;
 constexpr int VS_THREADS = VS_WARPS * 32;
 constexpr int VS_QCAP = 80;                   // queued runs per warp (>= 64: a tile end can add two per lane)
+constexpr int VS_REC = 3;                     // 16-byte words per queued run: key | sx, sy | sz, rb gn tl
 constexpr int VS_MAX_PROBES = 1 << 14;
 constexpr int VS_SUPER = 64;                  // tiles per super chunk of the octree replay's search (16384 points)
 
@@ -537,12 +549,12 @@ struct Run {
     uint64_t key;
     long long sx, sy, sz;      // sums of (coordinate - voxel origin) * 2^shift
     uint32_t rb, gn, tl;       // sum r | sum b << 16 ; sum g | count << 16 (<= 256 points) ; OR of the rgbt words
-    float f0, f1, f2;          // voxel coordinates
 };
 
 struct __align__(16) WarpStage {
     uint4 pts[2][VS_TILE];        // 8 KB: two stages of 256 points, 16-byte chunks XOR-swizzled inside every 128-byte row
-    uint4 queue[VS_QCAP * 4];     // 5 KB: closed runs waiting for their trip to the table
+    uint4 queue[VS_QCAP * VS_REC]; // 3.75 KB: closed runs waiting for their trip to the table
+    uint4 heads[32 * VS_REC];      // 1.5 KB: every lane's first run of the tile (it may continue the previous lane's last run)
 };
 
 struct StreamArgs {
@@ -587,10 +599,21 @@ __device__ __forceinline__ void run_add(Run &a, long long sx, long long sy, long
 }
 
 __device__ __forceinline__ void queue_store(uint4 *q, uint32_t pos, const Run &r) {
-    q[pos * 4 + 0] = make_uint4((uint32_t)r.key, (uint32_t)(r.key >> 32), (uint32_t)r.sx, (uint32_t)((unsigned long long)r.sx >> 32));
-    q[pos * 4 + 1] = make_uint4((uint32_t)r.sy, (uint32_t)((unsigned long long)r.sy >> 32), (uint32_t)r.sz, (uint32_t)((unsigned long long)r.sz >> 32));
-    q[pos * 4 + 2] = make_uint4(r.rb, r.gn, r.tl, 0u);
-    q[pos * 4 + 3] = make_uint4(__float_as_uint(r.f0), __float_as_uint(r.f1), __float_as_uint(r.f2), 0u);
+    q[pos * VS_REC + 0] = make_uint4((uint32_t)r.key, (uint32_t)(r.key >> 32), (uint32_t)r.sx, (uint32_t)((unsigned long long)r.sx >> 32));
+    q[pos * VS_REC + 1] = make_uint4((uint32_t)r.sy, (uint32_t)((unsigned long long)r.sy >> 32), (uint32_t)r.sz, (uint32_t)((unsigned long long)r.sz >> 32));
+    q[pos * VS_REC + 2] = make_uint4(r.rb, r.gn, r.tl, 0u);
+}
+__device__ __forceinline__ Run queue_load(const uint4 *q, uint32_t pos) {
+    const uint4 a = q[pos * VS_REC + 0], b = q[pos * VS_REC + 1], c = q[pos * VS_REC + 2];
+    Run r;
+    r.key = ((uint64_t)a.y << 32) | a.x;
+    r.sx = (long long)(((unsigned long long)a.w << 32) | a.z);
+    r.sy = (long long)(((unsigned long long)b.y << 32) | b.x);
+    r.sz = (long long)(((unsigned long long)b.w << 32) | b.z);
+    r.rb = c.x;
+    r.gn = c.y;
+    r.tl = c.z;
+    return r;
 }
 
 // ---- explicit state spaces: the table is global memory and the queue is shared memory, whatever the compiler can prove
@@ -622,8 +645,8 @@ struct DrainCtx { // by value: a reference to the kernel's parameter block would
 };
 
 // one queued run: find or claim its slot (the first probe `h` is already in flight), add the sums
-__device__ __forceinline__ void flush_run(const DrainCtx &c, bool active, uint64_t key, uint32_t slot, uint4 h, const uint4 &q0, const uint4 &q1, const uint4 &q2, const uint4 &q3,
-                                          bool &claimed, bool &lost, uint32_t &slot_out) {
+__device__ __forceinline__ void flush_run(const DrainCtx &c, bool active, uint64_t key, uint32_t slot, uint4 h, const uint4 &q0, const uint4 &q1, const uint4 &q2, bool &claimed,
+                                          bool &lost, uint32_t &slot_out) {
     claimed = false;
     lost = false;
     slot_out = slot;
@@ -660,11 +683,6 @@ __device__ __forceinline__ void flush_run(const DrainCtx &c, bool active, uint64
     red_add_u64(&sl->bn, (unsigned long long)(q2.x >> 16) | ((unsigned long long)(q2.y >> 16) << 32));
     const uint32_t tl = q2.z >> 24;
     if ((seen_tile & tl) != tl) red_or_u32(&sl->tile, tl);
-    if (claimed) {
-        sl->vx = __uint_as_float(q3.x);
-        sl->vy = __uint_as_float(q3.y);
-        sl->vz = __uint_as_float(q3.z);
-    }
 }
 
 // All 32 lanes: the queued runs go to the table, two runs per lane and pass with both 16-byte probes in flight together
@@ -682,34 +700,32 @@ __device__ __noinline__ uint32_t drain_queue(uint32_t qaddr, uint32_t qn, DrainC
     for (uint32_t base = 0; base < qn; base += 64) {
         const uint32_t r0 = base + lane, r1 = base + 32 + lane;
         const bool act0 = r0 < qn, act1 = r1 < qn;
-        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0, b0 = a0, b1 = a0, b2 = a0, b3 = a0, ha = a0, hb = a0;
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0, ha = a0, hb = a0;
         uint64_t keya = 0, keyb = 0;
         uint32_t slota = 0, slotb = 0;
         if (act0) {
-            a0 = lds_v4(qaddr + r0 * 64);
+            a0 = lds_v4(qaddr + r0 * (16 * VS_REC));
             keya = ((uint64_t)a0.y << 32) | a0.x;
             slota = hash_key(keya) & c.slot_mask;
             ha = ld_volatile_v4(&c.table[slota]);
         }
         if (act1) {
-            b0 = lds_v4(qaddr + r1 * 64);
+            b0 = lds_v4(qaddr + r1 * (16 * VS_REC));
             keyb = ((uint64_t)b0.y << 32) | b0.x;
             slotb = hash_key(keyb) & c.slot_mask;
             hb = ld_volatile_v4(&c.table[slotb]);
         }
         if (act0) {
-            a1 = lds_v4(qaddr + r0 * 64 + 16);
-            a2 = lds_v4(qaddr + r0 * 64 + 32);
-            a3 = lds_v4(qaddr + r0 * 64 + 48);
+            a1 = lds_v4(qaddr + r0 * (16 * VS_REC) + 16);
+            a2 = lds_v4(qaddr + r0 * (16 * VS_REC) + 32);
         }
         if (act1) {
-            b1 = lds_v4(qaddr + r1 * 64 + 16);
-            b2 = lds_v4(qaddr + r1 * 64 + 32);
-            b3 = lds_v4(qaddr + r1 * 64 + 48);
+            b1 = lds_v4(qaddr + r1 * (16 * VS_REC) + 16);
+            b2 = lds_v4(qaddr + r1 * (16 * VS_REC) + 32);
         }
         bool cla, clb, losta, lostb;
-        flush_run(c, act0, keya, slota, ha, a0, a1, a2, a3, cla, losta, slota);
-        flush_run(c, act1, keyb, slotb, hb, b0, b1, b2, b3, clb, lostb, slotb);
+        flush_run(c, act0, keya, slota, ha, a0, a1, a2, cla, losta, slota);
+        flush_run(c, act1, keyb, slotb, hb, b0, b1, b2, clb, lostb, slotb);
         if (__any_sync(FULL_MASK, losta || lostb)) {
             if (losta || lostb) red_or_u32(&c.header->pad[5], VS_FLAG_OVERFLOW);
         }
@@ -923,9 +939,10 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
 
         const uint32_t base = tile * VS_TILE;
         const uint32_t cnt = min((uint32_t)VS_TILE, a.n - base);
-        Run cur, head;
-        cur.key = 0; cur.sx = cur.sy = cur.sz = 0; cur.rb = cur.gn = cur.tl = 0; cur.f0 = cur.f1 = cur.f2 = 0.f;
-        head = cur;
+        Run cur;
+        cur.key = 0; cur.sx = cur.sy = cur.sz = 0; cur.rb = cur.gn = cur.tl = 0;
+        float cf0 = 0.f, cf1 = 0.f, cf2 = 0.f; // the open run's voxel coordinates
+        uint64_t head_key = 0;                 // key of the lane's first run once it is closed (its sums wait in ws.heads)
         bool have = false;
         int nclosed = 0;
         // state of the open run's leaf (octree modes): float bounds per axis, voxel origin, key bits
@@ -937,9 +954,12 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
             // chunk box of the tile (for the octree replay): a sweep of its own, so that the six extrema do not stay in
             // registers across the run loop
             float bmin0 = INFINITY, bmin1 = INFINITY, bmin2 = INFINITY, bmax0 = -INFINITY, bmax1 = -INFINITY, bmax2 = -INFINITY;
-            const float risk0 = tab.risk[0], risk1 = tab.risk[1], risk2 = tab.risk[2];
+            // a leaf face at (nearly) zero on some axis (the first point sits on a coordinate plane): floats within `risk` of
+            // it, other than an exact zero, are left to the two-pass path.  0 < |d| < risk  <=>  (bits(|d|) - 1) < (bits(risk) - 1)
+            // as unsigned integers; an axis without such a face has risk = 0 and never matches.
             const float fz0 = tab.fz[0], fz1 = tab.fz[1], fz2 = tab.fz[2];
-            const bool any_risk = risk0 > 0.f || risk1 > 0.f || risk2 > 0.f; // a leaf face at (nearly) zero: the first point sits on a coordinate plane
+            const uint32_t rk0 = __float_as_uint(tab.risk[0]) - 1u, rk1 = __float_as_uint(tab.risk[1]) - 1u, rk2 = __float_as_uint(tab.risk[2]) - 1u;
+            const bool any_risk = (tab.risk[0] > 0.f) | (tab.risk[1] > 0.f) | (tab.risk[2] > 0.f);
 #pragma unroll
             for (int j = 0; j < VS_L; j++) {
                 const uint4 raw = ws.pts[st][lane * VS_L + ((unsigned)j ^ (lane & 7u))];
@@ -948,9 +968,11 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
                     bmin0 = fminf(bmin0, x); bmax0 = fmaxf(bmax0, x);
                     bmin1 = fminf(bmin1, y); bmax1 = fmaxf(bmax1, y);
                     bmin2 = fminf(bmin2, z); bmax2 = fmaxf(bmax2, z);
-                    if (any_risk && ((fabsf(x - fz0) < risk0 && !(x == 0.f && fz0 == 0.f)) || (fabsf(y - fz1) < risk1 && !(y == 0.f && fz1 == 0.f)) ||
-                                     (fabsf(z - fz2) < risk2 && !(z == 0.f && fz2 == 0.f))))
-                        amb = true;
+                    if (any_risk) {
+                        const uint32_t ux = (__float_as_uint(x - fz0) & 0x7fffffffu) - 1u, uy = (__float_as_uint(y - fz1) & 0x7fffffffu) - 1u,
+                                       uz = (__float_as_uint(z - fz2) & 0x7fffffffu) - 1u;
+                        if ((tab.risk[0] > 0.f && ux < rk0) | (tab.risk[1] > 0.f && uy < rk1) | (tab.risk[2] > 0.f && uz < rk2)) amb = true;
+                    }
                 }
             }
 #pragma unroll
@@ -983,12 +1005,16 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
             const float f0 = floorf(__fmul_rn(p.x, inv)), f1 = floorf(__fmul_rn(p.y, inv)), f2 = floorf(__fmul_rn(p.z, inv));
             bool same_leaf = true;
             if (MODE != VS_LINEAR) same_leaf = p.x >= lo0 && p.x < hi0 && p.y >= lo1 && p.y < hi1 && p.z >= lo2 && p.z < hi2;
-            const bool same = have && same_leaf && f0 == cur.f0 && f1 == cur.f1 && f2 == cur.f2;
+            const bool same = have && same_leaf && f0 == cf0 && f1 == cf1 && f2 == cf2;
             const bool closing = valid && have && !same;
             const unsigned qm = __ballot_sync(FULL_MASK, closing && nclosed > 0);
             if (closing) {
-                if (nclosed == 0) head = cur;
-                else queue_store(ws.queue, qn + __popc(qm & lt), cur);
+                if (nclosed == 0) {
+                    queue_store(ws.heads, lane, cur);
+                    head_key = cur.key;
+                } else {
+                    queue_store(ws.queue, qn + __popc(qm & lt), cur);
+                }
                 nclosed++;
             }
             qn += __popc(qm);
@@ -1011,13 +1037,13 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
                     }
                     const int w0 = (int)f0 - org0, w1 = (int)f1 - org1, w2 = (int)f2 - org2;
                     if ((unsigned)w0 >= (unsigned)WL_RADIX || (unsigned)w1 >= (unsigned)WL_RADIX || (unsigned)w2 >= (unsigned)WL_RADIX) bad = true;
-                    cur.key = leafbits | (uint64_t)(uint32_t)((min(max(w2, 0), WL_RADIX - 1) * WL_RADIX + min(max(w1, 0), WL_RADIX - 1)) * WL_RADIX + min(max(w0, 0), WL_RADIX - 1));
+                    cur.key = leafbits | (uint64_t)(uint32_t)((w2 * WL_RADIX + w1) * WL_RADIX + w0); // (out of range: flagged above, the result is discarded)
                 }
                 cur.sx = cur.sy = cur.sz = 0;
                 cur.rb = cur.gn = cur.tl = 0;
-                cur.f0 = f0;
-                cur.f1 = f1;
-                cur.f2 = f2;
+                cf0 = f0;
+                cf1 = f1;
+                cf2 = f2;
                 od0 = (double)__fmul_rn(f0, a.cs);
                 od1 = (double)__fmul_rn(f1, a.cs);
                 od2 = (double)__fmul_rn(f2, a.cs);
@@ -1039,7 +1065,7 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
         const bool single = has_t && nclosed == 0;          // the whole segment is one run
         const uint64_t EMPTY_T = ~0ull, EMPTY_F = ~0ull - 1ull; // never valid keys (the low 19 bits of a key are < 72^3)
         const uint64_t tkey = has_t ? cur.key : EMPTY_T;
-        const uint64_t firstkey = !has_t ? EMPTY_F : (single ? cur.key : head.key);
+        const uint64_t firstkey = !has_t ? EMPTY_F : (single ? cur.key : head_key);
         const uint64_t prev_tkey = __shfl_up_sync(FULL_MASK, tkey, 1);
         const uint64_t next_first = __shfl_down_sync(FULL_MASK, firstkey, 1);
         const bool cont = lane > 0 && single && prev_tkey == cur.key;   // my (only) run continues the previous lane's tail run
@@ -1053,12 +1079,9 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
             const uint32_t trb = __shfl_up_sync(FULL_MASK, tail.rb, o), tgn = __shfl_up_sync(FULL_MASK, tail.gn, o), ttl = __shfl_up_sync(FULL_MASK, tail.tl, o);
             if ((int)lane - o >= seg_start) run_add(tail, tx, ty, tz, trb, tgn, ttl);
         }
-        {
-            // the run that ends where my segment starts: joined to my first run when that one is not my only run
-            const long long px = __shfl_up_sync(FULL_MASK, tail.sx, 1), py = __shfl_up_sync(FULL_MASK, tail.sy, 1), pz = __shfl_up_sync(FULL_MASK, tail.sz, 1);
-            const uint32_t prb = __shfl_up_sync(FULL_MASK, tail.rb, 1), pgn = __shfl_up_sync(FULL_MASK, tail.gn, 1), ptl = __shfl_up_sync(FULL_MASK, tail.tl, 1);
-            if (has_t && !single && lane > 0 && prev_tkey == head.key) run_add(head, px, py, pz, prb, pgn, ptl);
-        }
+        // the run that ends where my segment starts is joined to my first run when that one is not my only run
+        const long long px = __shfl_up_sync(FULL_MASK, tail.sx, 1), py = __shfl_up_sync(FULL_MASK, tail.sy, 1), pz = __shfl_up_sync(FULL_MASK, tail.sz, 1);
+        const uint32_t prb = __shfl_up_sync(FULL_MASK, tail.rb, 1), pgn = __shfl_up_sync(FULL_MASK, tail.gn, 1), ptl = __shfl_up_sync(FULL_MASK, tail.tl, 1);
         const bool push_tail = has_t && !absorbed, push_head = has_t && !single;
         const unsigned mt = __ballot_sync(FULL_MASK, push_tail), mh = __ballot_sync(FULL_MASK, push_head);
         if (qn + __popc(mt) + __popc(mh) > (uint32_t)VS_QCAP) { // the queue is drained when it is (nearly) full: dense passes
@@ -1067,9 +1090,12 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
         }
         if (push_tail) queue_store(ws.queue, qn + __popc(mt & lt), tail);
         qn += __popc(mt);
-        if (push_head) queue_store(ws.queue, qn + __popc(mh & lt), head);
+        if (push_head) {
+            Run head = queue_load(ws.heads, lane);
+            if (lane > 0 && prev_tkey == head_key) run_add(head, px, py, pz, prb, pgn, ptl);
+            queue_store(ws.queue, qn + __popc(mh & lt), head);
+        }
         qn += __popc(mh);
-
         __syncwarp();
     }
     cp_async_wait<0>();
@@ -1136,6 +1162,9 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
     __syncthreads();
     if (threadIdx.x == 0) {
         a.box_out->fallback = s_fallback;
+        a.box_out->m0[0] = s_m0[0];
+        a.box_out->m0[1] = s_m0[1];
+        a.box_out->m0[2] = s_m0[2];
         unsigned long long t_tail1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_tail1));
         a.box_out->tail_ns = t_tail1 - t_tail0;
@@ -1160,14 +1189,41 @@ __global__ void __launch_bounds__(256) voxel_words_kernel(const uint64_t *__rest
     words[c] = (key << cbits) | c;
 }
 
+// how to get a voxel's integer coordinates back from its key (they fix the origin its sums are relative to)
+struct EmitGeom {
+    int mode;        // VS_LINEAR: key = PCL's linear index; VS_TABLES: [Morton(leaf) | voxel-in-leaf]; VS_FUSED: [relative leaf x, y, z | voxel-in-leaf]
+    double mn[3];    // octree min corner the leaf indices count from (final box, or the first point's box)
+    double res, inv_cs;
+    int minb[3], div[3];
+};
+
+__device__ __forceinline__ void voxel_of_key(uint64_t key, const EmitGeom &g, float v[3]) {
+    if (g.mode == VS_LINEAR) {
+        const uint64_t dx = (uint64_t)g.div[0], dy = (uint64_t)g.div[1];
+        v[0] = (float)(g.minb[0] + (int)(key % dx));
+        v[1] = (float)(g.minb[1] + (int)((key / dx) % dy));
+        v[2] = (float)(g.minb[2] + (int)(key / (dx * dy)));
+        return;
+    }
+    const uint32_t wlin = (uint32_t)(key & ((1ull << WL_BITS) - 1ull));
+    const int w[3] = {(int)(wlin % WL_RADIX), (int)((wlin / WL_RADIX) % WL_RADIX), (int)(wlin / (WL_RADIX * WL_RADIX))};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        long long leaf;
+        if (g.mode == VS_FUSED) leaf = (long long)((key >> (WL_BITS + 15 * (2 - a))) & 0x7fff) - REL_BIAS;
+        else leaf = (long long)compact3((key >> WL_BITS) >> (2 - a));
+        v[a] = (float)(leaf_origin(g.mn[a], leaf, g.res, g.inv_cs) + w[a]); // the very expression the keys were made with
+    }
+}
+
 // mean xyz (exact sum, one rounding), truncated float colour average as pcl::CentroidPoint, OR of tiles
-__device__ __forceinline__ Point16 finalize_voxel(const VoxelSlot &s, float cs, double inv_scale) {
+__device__ __forceinline__ Point16 finalize_voxel(const VoxelSlot &s, const float v[3], float cs, double inv_scale) {
     Point16 o;
     const unsigned long long cnt = s.bn >> 32;
     const double dn = (double)cnt;
-    o.x = (float)((double)__fmul_rn(s.vx, cs) + ((double)(long long)s.sx * inv_scale) / dn);
-    o.y = (float)((double)__fmul_rn(s.vy, cs) + ((double)(long long)s.sy * inv_scale) / dn);
-    o.z = (float)((double)__fmul_rn(s.vz, cs) + ((double)(long long)s.sz * inv_scale) / dn);
+    o.x = (float)((double)__fmul_rn(v[0], cs) + ((double)(long long)s.sx * inv_scale) / dn);
+    o.y = (float)((double)__fmul_rn(v[1], cs) + ((double)(long long)s.sy * inv_scale) / dn);
+    o.z = (float)((double)__fmul_rn(v[2], cs) + ((double)(long long)s.sz * inv_scale) / dn);
     const float fn = (float)cnt;
     const uint32_t r = (uint32_t)__fdiv_rn((float)(s.rg & 0xffffffffull), fn) & 0xffu;
     const uint32_t g = (uint32_t)__fdiv_rn((float)(s.rg >> 32), fn) & 0xffu;
@@ -1178,12 +1234,14 @@ __device__ __forceinline__ Point16 finalize_voxel(const VoxelSlot &s, float cs, 
 
 // One output point per sorted list entry; the slot is read once and cleared, so the table is all zero
 // again when the kernel ends (no memset between calls).
-__global__ void __launch_bounds__(256) voxel_emit_kernel(const uint64_t *__restrict__ sorted, uint32_t v, uint32_t cmask, const uint32_t *__restrict__ list_slots, VoxelSlot *__restrict__ table,
-                                                          float cs, double inv_scale, cwipc_point *__restrict__ out, TableHeader *__restrict__ header) {
+__global__ void __launch_bounds__(256) voxel_emit_kernel(const uint64_t *__restrict__ sorted, uint32_t v, uint32_t cmask, const uint64_t *__restrict__ list_keys,
+                                                          const uint32_t *__restrict__ list_slots, VoxelSlot *__restrict__ table, EmitGeom geom, float cs, double inv_scale,
+                                                          cwipc_point *__restrict__ out, TableHeader *__restrict__ header) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) header->count = 0;
     if (j >= v) return;
-    VoxelSlot *sl = table + list_slots[(uint32_t)sorted[j] & cmask];
+    const uint32_t c = (uint32_t)sorted[j] & cmask;
+    VoxelSlot *sl = table + list_slots[c];
     uint4 *raw = reinterpret_cast<uint4 *>(sl);
     union {
         uint4 q[4];
@@ -1198,7 +1256,9 @@ __global__ void __launch_bounds__(256) voxel_emit_kernel(const uint64_t *__restr
     raw[1] = zero;
     raw[2] = zero;
     raw[3] = zero;
-    st_point(out, j, finalize_voxel(u.s, cs, inv_scale));
+    float vox[3];
+    voxel_of_key(list_keys[c], geom, vox);
+    st_point(out, j, finalize_voxel(u.s, vox, cs, inv_scale));
 }
 
 // a pass that failed half way: clear the claimed slots (the list knows them) and the header words
@@ -1234,6 +1294,10 @@ uint32_t *bbox_counter(int dev, cudaStream_t s) {
 }
 
 struct Plan {
+    Plan() {
+        memset(&kp, 0, sizeof(kp));
+        memset(&tables, 0, sizeof(tables));
+    }
     KeyParams kp;
     int keybits = 0;
     bool failed = false;
@@ -1564,9 +1628,19 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
             });
             const uint64_t *sorted = radix_sort_u64(words.as<uint64_t>(), other.as<uint64_t>(), v, cbits, cbits + keybits, dev, s);
             auto out = std::make_shared<Storage>(dev, v, s);
+            EmitGeom geom;
+            memset(&geom, 0, sizeof(geom));
+            geom.mode = fused ? VS_FUSED : (octree_split ? VS_TABLES : VS_LINEAR);
+            geom.res = args.res;
+            geom.inv_cs = 1.0 / (double)cellsize;
+            for (int a = 0; a < 3; a++) {
+                geom.mn[a] = fused ? ob.m0[a] : plan.kp.omin[a];
+                geom.minb[a] = plan.kp.minb[a];
+                geom.div[a] = std::max(1, plan.kp.div[a]);
+            }
             launch("voxel_emit_kernel", s, 16 * v, [&] {
-                voxel_emit_kernel<<<(unsigned)std::max<size_t>(1, div_up(v, 256)), 256, 0, s>>>(sorted, (uint32_t)v, (uint32_t)((1ull << cbits) - 1ull), list_slots.as<uint32_t>(), table, cellsize,
-                                                                                                inv_scale, out->d_pts, header);
+                voxel_emit_kernel<<<(unsigned)std::max<size_t>(1, div_up(v, 256)), 256, 0, s>>>(sorted, (uint32_t)v, (uint32_t)((1ull << cbits) - 1ull), list_keys.as<uint64_t>(),
+                                                                                                list_slots.as<uint32_t>(), table, geom, cellsize, inv_scale, out->d_pts, header);
             });
             out->count = v;
             // centroids lie inside the input's bounding box: hand it on so that a following filter need not recompute it
