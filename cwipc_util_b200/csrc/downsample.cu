@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
             }
         }
 
-#pragma unroll 1
+#pragma unroll 2
         for (int j = 0; j < VS_L; j++) {
             if (qn > (uint32_t)(VS_QCAP - 32)) {
                 drain(qn);
