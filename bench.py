@@ -3,11 +3,15 @@
 
 Metric (BASELINE.json): Mpoints/s for downsample + remove_outliers at 1/2/4/8 B200; % of HBM GB/s peak.
 
-Workload (BASELINE.json configs[4], the config the metric is quoted on): a sequence of 1M-point
+Workload (BASELINE.json configs[4], the config the metric is quoted on): a 240-frame sequence of 1M-point
 (1000 x 1000) 4-camera synthetic frames, per frame  cwipc_downsample(0.01) -> cwipc_remove_outliers(30, 1.0,
-perTile=False), frame-sharded over the GPUs with no collective on the data path.  240 frames at 8 GPUs =
-30 frames per GPU per step; scaling is WEAK (30 frames per GPU per step at every N).  A step is one pass
-over a rank's 30 frames.
+perTile=False), frame-sharded over the GPUs (frame f -> GPU f mod N) with no collective on the data path.
+Scaling is STRONG: the same 240 frames at every N (240 / N per GPU).  A step is PASSES (8) passes over the
+sequence, so that the timed region of K = 20 steps stays above half a second at 8 GPUs too.
+
+The same run also times BASELINE.json configs[3] on rank 0 (`config4` in the JSON line: one 8M-point cloud,
+cwipc_downsample at the five voxel sizes of the sweep and downsample(0.005) -> remove_outliers), the
+configuration the north-star HBM-roofline target is stated on.
 
     python bench.py --gpus 1 --steps 10 --warmup 3            # our arm (CUDA library through its C ABI)
     python bench.py --impl reference --gpus 1 ...             # the reference's CPU path (oracle port, all host cores)
@@ -41,7 +45,8 @@ sys.path.insert(0, REPO)
 POINTS_PER_FRAME = int(os.environ.get("BENCH_POINTS", 1000 * 1000))   # BENCH_POINTS: diagnostic only (host-bound or GPU-bound?)
 VOXEL = 0.01
 K, STDDEV = int(os.environ.get("BENCH_K", 30)), 1.0   # BENCH_K: diagnostic only
-FRAMES_PER_GPU = 30          # 240 frames / 8 GPUs
+SEQUENCE_FRAMES = 240        # configs[4]: the whole sequence, split over the GPUs
+PASSES = 8                   # passes over the sequence per step
 WORKERS = 15                 # host threads (one CUDA stream each) feeding one GPU; divides the 30 frames of a step
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -55,13 +60,17 @@ def log(*a):
 # --------------------------------------------------------------------------------------------------
 def make_frames(first, count, stride):
     """Frames first, first+stride, ...: same geometry, per-frame jitter/outliers seeded by the frame index."""
+    from concurrent.futures import ThreadPoolExecutor
     from cwipc_util_b200 import synthetic
     base = synthetic.simulate_cameras(synthetic.synthetic_cloud(POINTS_PER_FRAME), 4)
-    frames = []
-    for j in range(count):
+
+    def one(j):
         seed = first + j * stride
-        frames.append(synthetic.add_outliers(synthetic.add_noise(base, 0.002, seed), 0.005, seed))
-    return frames
+        return synthetic.add_outliers(synthetic.add_noise(base, 0.002, seed), 0.005, seed)
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with ThreadPoolExecutor(max(1, min(8, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))) as ex:
+        return list(ex.map(one, range(count)))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -164,14 +173,15 @@ class Worker(threading.Thread):
                 lib.cwipc_cuda_timer_start(timer)
                 # K steps back to back: a worker starts its share of step s+1 as soon as it has finished its share of
                 # step s (frames are independent), the timed region is bracketed once, around all K steps
-                for f in [f for _ in range(st["nsteps"]) for f in mine]:
+                for f in [f for _ in range(st["nsteps"] * st["passes"]) for f in mine]:
                     if mode == "resident":
                         o = self.frame_chain(st["device_frames"][f])
                         self.out_points += o.count()
                         o.free()
                     else:  # e2e: pinned host -> device -> filters -> pinned host
                         err = ctypes.c_char_p()
-                        p = lib.cwipc_from_points(st["host_ptrs"][f], POINTS_PER_FRAME * 16, POINTS_PER_FRAME, f, ctypes.byref(err), cw.CWIPC_API_VERSION)
+                        src = st["host_ptrs"][f] if mode == "e2e" else st["frames"][f].ctypes.data   # e2e_pageable: the caller's own (pageable) numpy memory
+                        p = lib.cwipc_from_points(src, POINTS_PER_FRAME * 16, POINTS_PER_FRAME, f, ctypes.byref(err), cw.CWIPC_API_VERSION)
                         if not p:
                             raise RuntimeError(f"cwipc_from_points failed: {err.value}")
                         pc = cw.cwipc_pointcloud_wrapper(p)
@@ -196,11 +206,12 @@ class Worker(threading.Thread):
                 pass
 
 
-def run_steps(workers, barrier, state, lib, mode, nsteps):
+def run_steps(workers, barrier, state, lib, mode, nsteps, passes=None):
     """Run nsteps steps in `mode` inside ONE timed region; returns its device time in ms: from the first worker
     stream's start event to the last one's stop event (host barrier + device synchronize on both sides)."""
     state["mode"] = mode
     state["nsteps"] = nsteps
+    state["passes"] = PASSES if passes is None else passes
     barrier.wait()
     barrier.wait()
     for w in workers:
@@ -271,6 +282,70 @@ def cpu_baseline_sample(frames, nframes):
     return nframes * POINTS_PER_FRAME / dt / 1e6, dt
 
 
+def measure_config4(cw, lib, peak):
+    """BASELINE.json configs[3] on one GPU: ONE 8M-point (2828 x 2828) cloud, cwipc_downsample at the five voxel sizes of the
+    sweep and downsample(0.005) -> remove_outliers(30, 1.0), device resident, CUDA-event timed around the C-ABI calls with the
+    L2 flushed before every call.  Two clouds: `synthetic` is the cloud as cwipc_synthetic generates it (SURVEY.md 8d config 4;
+    4-camera tile bits), `jittered` adds 2 mm noise and 0.5 % outliers (scan order no longer voxel-coherent).
+    frac = compulsory bytes (16 B per point in + 16 B per point out, per stage) / time / HBM peak."""
+    from cwipc_util_b200 import synthetic
+    n_req = 2828 * 2828
+    out = {"points": n_req, "hbm_peak_GBps": peak, "what": "configs[3]: one 8M-point cloud on one GPU (rank 0), median of 5 after 2 warm-ups, L2 flushed before every call", "clouds": {}}
+
+    def timed(fn, reps=5):
+        times, res = [], None
+        for i in range(reps + 2):
+            lib.cwipc_cuda_flush_l2()
+            cw.cuda_synchronize()
+            t = lib.cwipc_cuda_timer_create()
+            lib.cwipc_cuda_timer_start(t)
+            res = fn()
+            lib.cwipc_cuda_timer_stop(t)
+            cw.cuda_synchronize()
+            if i >= 2:
+                times.append(lib.cwipc_cuda_timer_elapsed_ms(t))
+            lib.cwipc_cuda_timer_destroy(t)
+        return float(np.median(times)), res
+
+    def profiled(fn):
+        lib.cwipc_cuda_profile_reset()
+        lib.cwipc_cuda_profile_enable(1)
+        lib.cwipc_cuda_flush_l2()
+        r = fn()
+        cw.cuda_synchronize()
+        lib.cwipc_cuda_profile_enable(0)
+        need = lib.cwipc_cuda_profile_report(None, 0)
+        buf = ctypes.create_string_buffer(need)
+        lib.cwipc_cuda_profile_report(buf, need)
+        prof = json.loads(buf.value.decode())
+        return r, {k: {"us": round(v["total_ms"] * 1e3, 1), "launches": v["launches"], "GBps": round(v["bytes"] / max(v["total_ms"], 1e-9) / 1e6, 1),
+                       "frac": round(v["bytes"] / max(v["total_ms"], 1e-9) / 1e6 / peak, 4)}
+                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"]) if k != "flush_kernel"}
+
+    base = synthetic.simulate_cameras(synthetic.synthetic_cloud(n_req), 4)
+    for name in ("synthetic", "jittered"):
+        pts = base if name == "synthetic" else synthetic.add_outliers(synthetic.add_noise(base, 0.002, 1), 0.005, 1)
+        n = len(pts)
+        pc = cw.cwipc_from_numpy_array(pts, 1)
+        pc._set_cellsize(synthetic.cellsize_of(n_req))
+        rows = []
+        for vs in (0.002, 0.005, 0.01, 0.02, 0.05):
+            ms, d = timed(lambda: cw.cwipc_downsample(pc, vs))
+            v = d.count()
+            _, kernels = profiled(lambda: cw.cwipc_downsample(pc, vs))
+            rows.append({"voxelsize": vs, "voxels": v, "ms": round(ms, 4), "Mpoints_per_s": round(n / ms / 1e3, 1), "compulsory_GBps": round(16.0 * (n + v) / ms / 1e6, 1),
+                         "frac": round(16.0 * (n + v) / ms / 1e6 / peak, 4), "kernels": kernels})
+        ms, res = timed(lambda: (lambda d: (d, cw.cwipc_remove_outliers(d, K, STDDEV, False)))(cw.cwipc_downsample(pc, 0.005)))
+        d, o = res
+        v, m = d.count(), o.count()
+        _, kernels = profiled(lambda: cw.cwipc_remove_outliers(cw.cwipc_downsample(pc, 0.005), K, STDDEV, False))
+        chain = {"what": "downsample(0.005) -> remove_outliers(30, 1.0, perTile=False)", "voxels": v, "kept": m, "ms": round(ms, 4), "Mpoints_per_s": round(n / ms / 1e3, 1),
+                 "frac": round(16.0 * (n + 2 * v + m) / ms / 1e6 / peak, 4), "kernels": kernels}
+        out["clouds"][name] = {"points": n, "downsample": rows, "chain": chain}
+        pc.free()
+    return out
+
+
 def run_ours(args):
     # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version banner)
     # is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
@@ -296,7 +371,8 @@ def run_ours(args):
         raise SystemExit("bench.py: libcwipc_util_cuda sees no CUDA device (there is no CPU fallback)")
     dev = local if cw.cuda_device_count() > local else 0
     cw.cuda_set_device(dev)
-    nframes = args.frames_per_gpu
+    # frame f of the 240-frame sequence goes to GPU f mod N (strong scaling); --frames-per-gpu overrides for diagnostics
+    nframes = args.frames_per_gpu if args.frames_per_gpu > 0 else len(range(rank, args.sequence_frames, world))
     cellsize = synthetic.cellsize_of(POINTS_PER_FRAME)
 
     t0 = time.perf_counter()
@@ -329,7 +405,7 @@ def run_ours(args):
     sampler.start()
     sampler.ready.wait(timeout=30)
     run_steps(workers, barrier, state, lib, "resident", args.warmup)
-    run_steps(workers, barrier, state, lib, "e2e", max(1, args.warmup // 2))
+    run_steps(workers, barrier, state, lib, "e2e", max(1, args.warmup // 2), passes=1)
     cw.cuda_synchronize()
     dist_barrier(dist, torch)
 
@@ -344,6 +420,10 @@ def run_ours(args):
     d2h_bytes = sum(w.d2h_bytes for w in workers)
     sampler.armed.clear()
     clocks = sampler.stop()
+    dist_barrier(dist, torch)
+    # the path an UNCHANGED reference caller takes: cwipc_from_points from its own pageable memory (python/cwipc/util.py
+    # passes ctypes / numpy buffers), one step of one pass
+    pageable_ms = run_steps(workers, barrier, state, lib, "e2e_pageable", 1, passes=1)
     dist_barrier(dist, torch)
 
     # ---- roofline: the same frames once more on ONE stream with events around every launch, so that the
@@ -374,13 +454,19 @@ def run_ours(args):
     total_e2e_ms = dist_reduce(dist, torch, e2e_ms, "MAX")
     launches_all = dist_reduce(dist, torch, launches, "SUM")
     d2h_all = dist_reduce(dist, torch, d2h_bytes, "SUM")
-    points_per_step = nframes * POINTS_PER_FRAME * world
+    total_pageable_ms = dist_reduce(dist, torch, pageable_ms, "MAX")
+    frames_all = int(dist_reduce(dist, torch, nframes, "SUM"))            # the whole sequence
+    points_per_step = frames_all * PASSES * POINTS_PER_FRAME
     value = points_per_step * args.steps / (total_ms / 1e3) / 1e6
     e2e_value = points_per_step * args.steps / (total_e2e_ms / 1e3) / 1e6
+    pageable_value = frames_all * POINTS_PER_FRAME / (total_pageable_ms / 1e3) / 1e6
 
     if rank != 0:
+        dist_barrier(dist, torch)      # rank 0 times configs[3] meanwhile
         return
     peak, peak_src = measured_hbm_peak()
+    config4 = measure_config4(cw, lib, peak) if not args.skip_config4 else None
+    dist_barrier(dist, torch)
     roofline = None
     if prof:
         name, rec = max(prof.items(), key=lambda kv: kv[1]["total_ms"])
@@ -406,7 +492,8 @@ def run_ours(args):
             kernels[k] = {"launches_per_frame": round(v["launches"] / nprof, 2), "us_per_launch": round(v["total_ms"] * 1e3 / max(1, v["launches"]), 2),
                           "GBps": round(gbs, 1), "frac": round(gbs / peak, 4), "share": round(v["total_ms"] / step_kernel_ms, 3)}
         roofline = {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": traffic, "issue": issue, "peak_source": peak_src, "launches": rec["launches"], "avg_launch_us": round(rec["total_ms"] * 1e3 / max(1, rec["launches"]), 2),
+                    "traffic": traffic, "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum per launch from the latest ncu --set full capture (profiles/traffic.json), not measured in this run",
+                    "issue": issue, "peak_source": peak_src, "launches": rec["launches"], "avg_launch_us": round(rec["total_ms"] * 1e3 / max(1, rec["launches"]), 2),
                     "algorithmic_bytes_per_launch": int(rec["bytes"] / max(1, rec["launches"])), "share_of_step_kernel_time": round(rec["total_ms"] / step_kernel_ms, 3),
                     "how": f"{nprof} of the step's frames replayed on one stream, CUDA events around every launch (cwipc_cuda_profile_*)",
                     "note": "the kNN kernels are instruction-issue bound (exact top-(k+1) selection over ~300 candidates per query), not HBM bound: "
@@ -414,7 +501,7 @@ def run_ours(args):
                     "kernels": kernels}
         # whole-op roofline on compulsory bytes: 16 B in + 16 B out per stage
         # downsample: 16 N in + 16 V out; remove_outliers: 16 V in + 16 M out   (per rank and step)
-        compulsory = 16.0 * (nframes * POINTS_PER_FRAME + 2 * mid_points + out_points)
+        compulsory = 16.0 * (nframes * PASSES * POINTS_PER_FRAME + 2 * mid_points + out_points)
         roofline["op_compulsory_GBps_per_gpu"] = round(compulsory / (resident_ms / args.steps / 1e3) / 1e9, 1)
         roofline["op_compulsory_frac"] = round(roofline["op_compulsory_GBps_per_gpu"] / peak, 4)
 
@@ -422,14 +509,19 @@ def run_ours(args):
     line = {
         "metric": "Mpoints/s for downsample+remove_outliers at 1/2/4/8 B200; % of HBM GB/s peak",
         "value": round(value, 1), "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(total_ms / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 keys/distances, int64 fixed-point sums, f64 statistics", "data": "synthetic",
-        "config": {"workload": "configs[4]: 1M-point 4-camera synthetic frames, per frame cwipc_downsample(0.01) -> cwipc_remove_outliers(30,1.0,perTile=False); "
-                               f"{nframes} frames per GPU per step, frame-sharded, no collective", "points_per_frame": POINTS_PER_FRAME, "frames_per_gpu_per_step": nframes,
-                   "host_threads_per_gpu": nworkers, "host_cores": cores, "host_wait": "poll %s us then nap %s us" % (os.environ.get("CWIPC_CUDA_SPIN_US", "20"), os.environ.get("CWIPC_CUDA_SLEEP_US", "20")), "l2": f"inputs larger than L2 ({nframes} x 16 MB per GPU per step, each frame touched once per step)",
+        "config": {"workload": f"configs[4]: {frames_all}-frame sequence of 1M-point 4-camera synthetic frames, per frame cwipc_downsample(0.01) -> cwipc_remove_outliers(30,1.0,perTile=False); "
+                               f"frame f on GPU f mod N (strong scaling: the same {frames_all} frames at every N), no collective; a step = {PASSES} passes over the sequence",
+                   "points_per_frame": POINTS_PER_FRAME, "sequence_frames": frames_all, "passes_per_step": PASSES, "frames_per_gpu": nframes,
+                   "host_threads_per_gpu": nworkers, "host_cores": cores, "host_wait": "poll %s us then nap %s us" % (os.environ.get("CWIPC_CUDA_SPIN_US", "20"), os.environ.get("CWIPC_CUDA_SLEEP_US", "20")),
+                   "l2": f"inputs larger than L2 ({nframes} x 16 MB per GPU per pass, each frame touched once per pass)",
                    "parallelism": f"frames x{world}"},
         "e2e": {"value": round(e2e_value, 1), "unit": "Mpoints/s", "h2d_bytes_per_step": points_per_step * 16, "d2h_bytes_per_step": int(d2h_all / max(1, args.steps)),
-                "ms_per_step": round(total_e2e_ms / args.steps, 3)},
+                "ms_per_step": round(total_e2e_ms / args.steps, 3), "host_memory": "page-locked (cwipc_cuda_host_alloc)",
+                "pageable": {"value": round(pageable_value, 1), "unit": "Mpoints/s", "what": "the same chain with cwipc_from_points reading the caller's pageable numpy memory, as an unchanged "
+                             "python/cwipc/util.py caller supplies it; one pass over the sequence", "ms": round(total_pageable_ms, 3)}},
+        "config4": config4,
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": roofline,
@@ -456,8 +548,8 @@ def run_reference(args):
     oracle.load()
     cores = os.cpu_count() or 1
     nthreads = max(1, cores)
-    per_step = nthreads  # one frame per host thread per step: a bounded sample of the 30*N-frame step
-    frames = make_frames(0, min(per_step, 8), 1)
+    per_step = nthreads  # one frame per host thread per step: a bounded sample of the 8 x 240-frame step
+    frames = make_frames(0, min(per_step, 16), 1)
     cellsize = synthetic.cellsize_of(POINTS_PER_FRAME)
 
     def one(i):
@@ -478,7 +570,7 @@ def run_reference(args):
         "impl": "reference",
         "metric": "Mpoints/s for downsample+remove_outliers at 1/2/4/8 B200; % of HBM GB/s peak",
         "value": round(value, 3), "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32/f64 (CPU)", "data": "synthetic",
         "config": {"workload": "configs[4]: 1M-point 4-camera synthetic frames, per frame cwipc_downsample(0.01) -> cwipc_remove_outliers(30,1.0,perTile=False)",
                    "points_per_frame": POINTS_PER_FRAME, "frames_per_step": per_step, "parallelism": f"{nthreads} host threads, one frame each"},
@@ -495,7 +587,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--sequence-frames", type=int, default=SEQUENCE_FRAMES)
+    ap.add_argument("--frames-per-gpu", type=int, default=0, help="diagnostics: this many frames on every GPU instead of its share of the sequence")
+    ap.add_argument("--skip-config4", action="store_true", help="diagnostics: leave out the 8M-point configs[3] measurement")
     ap.add_argument("--workers", type=int, default=0, help="host threads per GPU (0 = choose from the core count)")
     ap.add_argument("--cpu-frames", type=int, default=24)
     args = ap.parse_args()
