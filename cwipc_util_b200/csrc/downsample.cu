@@ -1436,7 +1436,8 @@ void launch_stream(const StreamArgs &args, const KeyTables &tab, int dev, cudaSt
         CWCU_CHECK(cudaFuncSetAttribute(voxel_stream_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); // two blocks per SM
     });
     // persistent warps: two blocks of eight warps per SM, every warp takes tiles gw, gw + nw, ...
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up((size_t)args.ntiles, (size_t)VS_WARPS), (size_t)sm_count(dev) * 2));
+    static const size_t tiles_per_warp = [] { const char *e = getenv("CWIPC_CUDA_DS_TILES_PER_WARP"); return (size_t)std::max(1, e && *e ? atoi(e) : 1); }(); // tuning only
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up((size_t)args.ntiles, (size_t)VS_WARPS * tiles_per_warp), (size_t)sm_count(dev) * 2));
     launch("voxel_stream_kernel", s, 16 * (size_t)args.n, [&] { voxel_stream_kernel<MODE><<<grid, VS_THREADS, VS_SMEM_BYTES, s>>>(args, tab); });
 }
 

@@ -210,8 +210,8 @@ struct FarEntry {
 };
 
 // ---- main pass: one warp per 32 consecutive (cell-ordered) queries, one lane per query ---------------
-// Queries that share a level-2 node (a 4x4x4 block of cells) are processed together: their candidate
-// set is every cell within rc pitches of their common bounding box (at most 6x6x6 cells).  Lane 0
+// Queries that share a level-1 node (a 2x2x2 block of cells) are processed together: their candidate
+// set is every cell within rc pitches of their common bounding box (at most 4x4x4 cells).  Lane 0
 // streams the candidates' 16-byte records into a double-buffered shared-memory ring with TMA bulk
 // copies (one per contiguous cell range); every lane then scans the same records as broadcast 128-bit
 // shared loads.  Per lane, distances below the running (k+1)-th best are parked in a shared-memory
@@ -221,14 +221,17 @@ constexpr int KT_WARPS = 2;  // small blocks: a block's registers and shared mem
 constexpr int KT_THREADS = KT_WARPS * 32;
 constexpr int KT_CH = 128;     // candidates per stage
 constexpr int KT_STAGES = 2;
-constexpr int KT_MAXR = 216;   // cells of the largest candidate box: 6x6x6 (a 4-cell group span + rc <= 1 on both sides)
+constexpr int KT_GROUP_LEVEL = 2; // queries are grouped by level-1 node (2x2x2 cells): ~one warp of queries per group on surface data, and a
+                                  // candidate box of 4x4x4 cells instead of the 6x6x6 a level-2 group needs (3.4x fewer candidates per query)
+constexpr int KT_GROUP_SPAN = 1 << KT_GROUP_LEVEL;
+constexpr int KT_MAXR = (KT_GROUP_SPAN + 2) * (KT_GROUP_SPAN + 2) * (KT_GROUP_SPAN + 2); // cells of the largest candidate box (rc <= 1 on both sides)
 constexpr int KT_BUF = 16;     // parked distances per lane
 constexpr int KT_BLOCKS_PER_SM = 12; // register budget 85/thread (24 warps per SM): more resident warps hide the scan's latency
 
 struct __align__(128) KnnWarpSmem {
     Point16 cand[KT_STAGES][KT_CH]; // 4096 B
     float buf[KT_BUF][32];          // 2048 B
-    uint2 ranges[KT_MAXR];          // 4096 B
+    uint2 ranges[KT_MAXR];          // 512 B
     uint64_t mbar[KT_STAGES];
 };
 
@@ -280,8 +283,8 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
         const Point16 q = spts16[qs];
         const float ux = cell_u(q.x, gp.gmin[0], gp.inv_h), uy = cell_u(q.y, gp.gmin[1], gp.inv_h), uz = cell_u(q.z, gp.gmin[2], gp.inv_h);
 
-        // groups: runs of lanes inside one level-2 node (codes are non-decreasing along the lanes)
-        const uint64_t node2 = code >> 6;
+        // groups: runs of lanes inside one level-KT_GROUP_LEVEL node (codes are non-decreasing along the lanes)
+        const uint64_t node2 = code >> (3 * KT_GROUP_LEVEL);
         const uint64_t prev_node2 = __shfl_up_sync(FULL_MASK, node2, 1);
         const unsigned heads = __ballot_sync(FULL_MASK, (lane == 0) || (node2 != prev_node2));
         const int m = __popc(heads);
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
                 const int cy0 = max((int)floorf(loy - rc), 0), cy1 = min((int)floorf(hiy + rc), gp.gdim[1] - 1);
                 const int cz0 = max((int)floorf(loz - rc), 0), cz1 = min((int)floorf(hiz + rc), gp.gdim[2] - 1);
                 const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1, nbz = cz1 - cz0 + 1;
-                const int nb = nbx * nby * nbz; // <= 6*6*6: the queries span at most 4 cells per axis and rc <= 1
+                const int nb = nbx * nby * nbz; // <= KT_MAXR: the queries span at most KT_GROUP_SPAN cells per axis and rc <= 1
                 const float rc2 = rc * rc;
                 // cells that overlap the queries' box first: their points tighten the running bound early,
                 // so most candidates of the surrounding shell fail the threshold test without being parked
