@@ -28,6 +28,11 @@ float min_distance_to_first(const cwipc_point *in, size_t n, cudaStream_t s);
 // distinct tile values in first-appearance order. ref: src/cwipc_filters.cpp:239-249
 std::vector<int> tiles_in_first_appearance_order(const cwipc_point *in, size_t n, cudaStream_t s);
 
+// The reference's synthetic cloud (src/cwipc_synthetic.cpp:182-222) generated in HBM: side x side points, row hi at height
+// hi * dh, column ai at angle ai * da.  d_radius[hi] (float), d_sin[ai] / d_cos[ai] (double) are the host's own libm values
+// (3 * side numbers), so the geometry is bit-identical to the host generator; colours use the device's double sin.
+void synthetic_points(cwipc_point *out, int side, float dh, float da, const float *d_radius, const double *d_sin, const double *d_cos, float angle, bool eyes_lit, cudaStream_t s);
+
 // ---- downsample.cu -------------------------------------------------------------------------
 struct DownsampleResult {
     StoragePtr out;    // nullptr on failure

@@ -314,4 +314,43 @@ void flush_l2(int dev, cudaStream_t s) {
     check_launch("flush_kernel");
 }
 
+// ---- synthetic source: the points are made where they are used -------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) synthetic_kernel(cwipc_point *__restrict__ out, int side, float dh, float da, const float *__restrict__ radius_tab,
+                                                         const double *__restrict__ sin_tab, const double *__restrict__ cos_tab, float angle, int eyes_lit) {
+    const float pi = 3.14159265358979f;
+    const uint32_t n = (uint32_t)side * (uint32_t)side;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int hi = (int)(i / (uint32_t)side), ai = (int)(i % (uint32_t)side);
+        const float h = __fmul_rn((float)hi, dh), a = __fmul_rn((float)ai, da);
+        const float radius = radius_tab[hi];
+        const float px = (float)((double)radius * sin_tab[ai]);
+        const float pz = (float)((double)radius * cos_tab[ai]);
+        uint32_t c[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            // (k + 2) * pi * h + angle + a, every operation in float as the host compiler evaluates it
+            const float arg = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn((float)(k + 2), pi), h), angle), a);
+            const float v = (float)((1.0 + sin((double)arg)) / 2.0);
+            c[k] = (uint32_t)(int)((double)v * 255.0);
+        }
+        const bool in_eye = h > 1.7f && h < 1.8f && (((double)a > (double)pi * 0.083 && (double)a < (double)pi * 0.1667) || ((double)a > (double)pi * 1.833 && (double)a < (double)pi * 1.917));
+        if (in_eye && eyes_lit) c[0] = c[1] = c[2] = 255u;
+        Point16 p;
+        p.x = -px;
+        p.y = h;
+        p.z = pz;
+        p.rgbt = (c[0] & 0xffu) | ((c[1] & 0xffu) << 8) | ((c[2] & 0xffu) << 16) | ((pz < 0.f ? 1u : 2u) << 24);
+        st_point(out, i, p);
+    }
+}
+} // namespace
+
+void synthetic_points(cwipc_point *out, int side, float dh, float da, const float *d_radius, const double *d_sin, const double *d_cos, float angle, bool eyes_lit, cudaStream_t s) {
+    const size_t n = (size_t)side * side;
+    if (n == 0) return;
+    const unsigned grid = (unsigned)std::min<size_t>(div_up(n, 256), 148 * 16);
+    launch("synthetic_kernel", s, 16 * n, [&] { synthetic_kernel<<<grid, 256, 0, s>>>(out, side, dh, da, d_radius, d_sin, d_cos, angle, eyes_lit ? 1 : 0); });
+}
+
 } // namespace cwcu

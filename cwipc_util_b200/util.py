@@ -327,6 +327,16 @@ class cwipc_activesource_wrapper:
         a, b = ctypes.c_float(angle), ctypes.c_float(0)
         return cwipc_util_dll_load().cwipc_activesource_auxiliary_operation(self._src, b"test-setangle", ctypes.byref(a), 4, ctypes.byref(b), 4)
 
+    def host_generate(self, angle: float, npoints: int) -> numpy.ndarray:
+        """libcwipc_util_cuda only: the HOST generator's points for `angle` (the checker of the device-side generator);
+        the next get() uses the same angle instead of the wall clock."""
+        a = ctypes.c_float(angle)
+        out = numpy.zeros(npoints, cwipc_point_numpy_dtype)
+        ok = cwipc_util_dll_load().cwipc_activesource_auxiliary_operation(self._src, b"cuda-host-generate", ctypes.byref(a), 4, out.ctypes.data, out.nbytes)
+        if not ok:
+            raise CwipcError("cuda-host-generate refused (wrong point count?)")
+        return out
+
 
 # ---- module functions, same names as the reference binding -------------------------------------
 def cwipc_get_version() -> str:

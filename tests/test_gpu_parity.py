@@ -672,3 +672,23 @@ def test_downsample_first_point_on_coordinate_planes(cw, orc):
     for voxel in (0.005, 0.02):
         want, cs, _, counts = orc.downsample(tiny, voxel, 0.0)
         assert_points_close(download(cw.cwipc_downsample(upload(cw, tiny), voxel)), want, cs)
+
+
+@pytest.mark.parametrize("npoints,angle", [(160000, 0.0), (160000, 1.7), (250000, 0.33), (1000000, 12.5), (7, 0.1)])
+def test_synthetic_source_generates_on_the_device(cw, npoints, angle):
+    """ref: src/cwipc_synthetic.cpp:182-222.  The source makes its points in HBM from 3 * sqrt(N) host-computed libm values
+    (no host-to-device copy of points); the bytes equal the host generator's, which stays reachable as the checker."""
+    gen = cw.cwipc_synthetic(0, npoints)
+    assert gen.start()
+    side = int(np.sqrt(npoints))
+    want = gen.host_generate(angle, side * side)
+    pc = gen.get()
+    assert pc.count() == side * side and pc.cellsize() == np.float32(2.0 / side)
+    got = download(pc)
+    for a in "xyz":   # geometry: bit-identical by construction (the host's own sin / cos / pow values, expanded on the device)
+        assert np.array_equal(got[a].view(np.uint32), want[a].view(np.uint32)), a
+    assert np.array_equal(got["tile"], want["tile"])
+    for c in "rgb":   # colours use the device's double-precision sin (2 ulp): equal except, at worst, an LSB once in ~1e7 values
+        diff = np.abs(got[c].astype(int) - want[c].astype(int))
+        assert diff.max(initial=0) <= 1 and np.count_nonzero(diff) <= 1
+    gen.free()
