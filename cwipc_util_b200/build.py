@@ -36,6 +36,7 @@ SOURCES = [
     "logging.cpp",
     "pointcloud.cpp",
     "filters.cpp",
+    "slab.cpp",
     "abi.cpp",
     "synthetic.cpp",
     "ply.cpp",

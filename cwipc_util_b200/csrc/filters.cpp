@@ -140,8 +140,9 @@ cwipc_pointcloud *cwipc_join(cwipc_pointcloud *pc1, cwipc_pointcloud *pc2) {
         out->count = a->count + b->count;
         if (a->count) CWCU_CHECK(cudaMemcpyAsync(out->d_pts, a->d_pts, a->count * sizeof(cwipc_point), cudaMemcpyDeviceToDevice, s));
         if (b->count) {
-            // a cloud on another device is reachable through peer copy (UVA)
-            CWCU_CHECK(cudaMemcpyAsync(out->d_pts + a->count, b->d_pts, b->count * sizeof(cwipc_point), cudaMemcpyDefault, s));
+            // a cloud on another device: an explicit peer copy (memory of a private pool is not reachable through UVA alone)
+            if (b->dev != dev) CWCU_CHECK(cudaMemcpyPeerAsync(out->d_pts + a->count, dev, b->d_pts, b->dev, b->count * sizeof(cwipc_point), s));
+            else CWCU_CHECK(cudaMemcpyAsync(out->d_pts + a->count, b->d_pts, b->count * sizeof(cwipc_point), cudaMemcpyDeviceToDevice, s));
         }
         out->mark_ready();
         a->release_after_read(s);

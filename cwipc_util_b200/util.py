@@ -185,6 +185,14 @@ def cwipc_util_dll_load(libname: Optional[str] = None) -> ctypes.CDLL:
         "cwipc_cuda_profile_report": ([ctypes.c_char_p, ctypes.c_size_t], ctypes.c_size_t),
         "cwipc_cuda_flush_l2": ([], None),
         "cwipc_cuda_trim": ([], ctypes.c_int),
+        "cwipc_cuda_comm_unique_id": ([ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_comm_create": ([ctypes.c_void_p, ctypes.c_int, ctypes.c_int], ctypes.c_void_p),
+        "cwipc_cuda_comm_free": ([ctypes.c_void_p], None),
+        "cwipc_cuda_comm_rank": ([ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_comm_size": ([ctypes.c_void_p], ctypes.c_int),
+        "cwipc_cuda_slab_downsample": ([cwipc_pointcloud_p, ctypes.c_float, ctypes.c_void_p], cwipc_pointcloud_p),
+        "cwipc_cuda_slab_remove_outliers": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_float, ctypes.c_bool, ctypes.c_float, ctypes.c_void_p], cwipc_pointcloud_p),
+        "cwipc_cuda_slab_tilefilter": ([cwipc_pointcloud_p, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)], cwipc_pointcloud_p),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(d, name)
@@ -661,3 +669,39 @@ class cuda_distances:
         if not rv:
             raise CwipcError("cwipc_cuda_distances_filter failed")
         return cwipc_pointcloud_wrapper(rv)
+
+
+# ---- one cloud partitioned over several GPUs: the library's own NCCL protocol (csrc/slab.cpp) -----------------------
+class cuda_comm:
+    """cwipc_cuda_comm: one rank of a group of processes (or threads), one GPU each.  `unique_id` (128 bytes from
+    cuda_comm.unique_id() on one rank) has to reach every rank by the caller's own means; size 1 needs none."""
+
+    def __init__(self, unique_id: Optional[bytes], nranks: int, rank: int):
+        buf = ctypes.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._c = cwipc_util_dll_load().cwipc_cuda_comm_create(buf, nranks, rank)
+        if not self._c:
+            raise CwipcError("cwipc_cuda_comm_create failed (NCCL not found, or ncclCommInitRank failed)")
+        self.rank, self.size = rank, nranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        if cwipc_util_dll_load().cwipc_cuda_comm_unique_id(buf) != 0:
+            raise CwipcError("cwipc_cuda_comm_unique_id failed (libnccl.so.2 not found?)")
+        return buf.raw
+
+    def free(self) -> None:
+        if self._c:
+            cwipc_util_dll_load().cwipc_cuda_comm_free(self._c)
+            self._c = None
+
+    def downsample(self, pc: cwipc_pointcloud_wrapper, voxelsize: float) -> cwipc_pointcloud_wrapper:
+        return cwipc_pointcloud_wrapper(cwipc_util_dll_load().cwipc_cuda_slab_downsample(pc.as_cwipc_p(), voxelsize, self._c))
+
+    def remove_outliers(self, pc: cwipc_pointcloud_wrapper, kNeighbors: int, stddevMulThresh: float, perTile: bool = False, halo: float = 0.0) -> cwipc_pointcloud_wrapper:
+        return cwipc_pointcloud_wrapper(cwipc_util_dll_load().cwipc_cuda_slab_remove_outliers(pc.as_cwipc_p(), kNeighbors, stddevMulThresh, perTile, halo, self._c))
+
+    def tilefilter(self, pc: cwipc_pointcloud_wrapper, tile: int):
+        off, tot = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        rv = cwipc_pointcloud_wrapper(cwipc_util_dll_load().cwipc_cuda_slab_tilefilter(pc.as_cwipc_p(), tile, self._c, ctypes.byref(off), ctypes.byref(tot)))
+        return rv, off.value, tot.value

@@ -381,6 +381,30 @@ _CWIPC_UTIL_EXPORT void cwipc_cuda_profile_enable(int on);
 _CWIPC_UTIL_EXPORT void cwipc_cuda_profile_reset(void);
 _CWIPC_UTIL_EXPORT size_t cwipc_cuda_profile_report(char *buf, size_t size);
 /* Overwrite a buffer larger than L2 on the calling thread's stream (bench hygiene). */
+/* ---- one cloud partitioned over several GPUs as x-slabs (BASELINE configs[3]) --------------------------------------------
+ * One process (or thread) per GPU; the WHOLE cloud is the concatenation of the ranks' parts in rank order, every call below
+ * is collective (all ranks call it with their part) and returns this rank's part of what the single-GPU filter returns on
+ * the whole cloud.  Points travel with ncclSend / ncclRecv between device buffers, metadata with small all-gathers, all on
+ * the calling thread's stream.  libnccl.so.2 is loaded with dlopen on first use ($CWIPC_CUDA_NCCL_LIBRARY overrides).
+ * A communicator of size 1 needs no NCCL and no id. */
+typedef struct cwipc_cuda_comm cwipc_cuda_comm;
+/* 128 bytes (ncclUniqueId) made on one rank, to be handed to every rank by the caller's own means.  0 on success. */
+_CWIPC_UTIL_EXPORT int cwipc_cuda_comm_unique_id(void *id128);
+/* collective: ncclCommInitRank on the calling thread's current device.  NULL on error. */
+_CWIPC_UTIL_EXPORT cwipc_cuda_comm *cwipc_cuda_comm_create(const void *id128, int nranks, int rank);
+_CWIPC_UTIL_EXPORT void cwipc_cuda_comm_free(cwipc_cuda_comm *comm);
+_CWIPC_UTIL_EXPORT int cwipc_cuda_comm_rank(cwipc_cuda_comm *comm);
+_CWIPC_UTIL_EXPORT int cwipc_cuda_comm_size(cwipc_cuda_comm *comm);
+/* ref: src/cwipc_filters.cpp:89-172.  Bit-identical (as a set of records) to cwipc_downsample of the whole cloud; rank r
+ * holds the voxels of its x-slab, in the reference's order. */
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_slab_downsample(cwipc_pointcloud *pc, float voxelsize, cwipc_cuda_comm *comm);
+/* ref: src/cwipc_filters.cpp:181-278.  halo <= 0: chosen from the cellsize metadata (results never depend on it).  perTile:
+ * one pass per tile value in the order of first appearance in the whole cloud; this rank's pieces in that order. */
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_slab_remove_outliers(cwipc_pointcloud *pc, int kNeighbors, float stddevMulThresh, bool perTile, float halo, cwipc_cuda_comm *comm);
+/* ref: src/cwipc_filters.cpp:281-306.  This rank's piece; *global_offset / *global_count (may be NULL): where it sits in, and
+ * the size of, the whole result (all-gather of the counts). */
+_CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_cuda_slab_tilefilter(cwipc_pointcloud *pc, int tile, cwipc_cuda_comm *comm, uint64_t *global_offset, uint64_t *global_count);
+
 _CWIPC_UTIL_EXPORT void cwipc_cuda_flush_l2(void);
 /* Hand cached device memory of the calling thread's current device back to the driver (the library's private memory pool,
  * the calling thread's scratch arena and voxel-table workspace, those of exited threads).  Waits for the device to go idle.

@@ -148,7 +148,44 @@ class NumpyOps:
         pass
 
 
+def run_rank_lib(rank, world, port, indir, outdir, voxelsize, k, mul, cellsize, halo):
+    """The protocol INSIDE libcwipc_util_cuda (csrc/slab.cpp: NCCL through dlopen, one GPU per rank).  torch.distributed
+    (gloo) only carries the 128-byte ncclUniqueId from rank 0 to the others."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import cwipc_util_b200 as cw
+    from cwipc_util_b200 import util
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cw.cuda_set_device(rank)
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(util.cuda_comm.unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(uid, src=0)
+    comm = util.cuda_comm(bytes(uid.numpy().tobytes()), world, rank)
+    part = numpy.load(os.path.join(indir, f"part{rank}.npy"))
+    pc = cw.cwipc_from_numpy_array(part, 7)
+    pc._set_cellsize(cellsize)
+    ds = comm.downsample(pc, voxelsize)
+    numpy.save(os.path.join(outdir, f"ds{rank}.npy"), ds.get_numpy_array().copy())
+    kept = comm.remove_outliers(pc, k, mul, False, halo or 0.0)
+    numpy.save(os.path.join(outdir, f"sor{rank}.npy"), kept.get_numpy_array().copy())
+    chain = comm.remove_outliers(ds, k, mul, False, 0.0)
+    numpy.save(os.path.join(outdir, f"chain{rank}.npy"), chain.get_numpy_array().copy())
+    pertile = comm.remove_outliers(pc, k, mul, True, halo or 0.0)
+    numpy.save(os.path.join(outdir, f"pertile{rank}.npy"), pertile.get_numpy_array().copy())
+    tf, off, tot = comm.tilefilter(pc, 2)
+    numpy.save(os.path.join(outdir, f"tf{rank}.npy"), tf.get_numpy_array().copy())
+    numpy.save(os.path.join(outdir, f"tfmeta{rank}.npy"), numpy.array([off, tot], numpy.int64))
+    comm.free()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_rank(rank, world, port, backend, indir, outdir, voxelsize, k, mul, cellsize, halo):
+    if backend == "lib":
+        return run_rank_lib(rank, world, port, indir, outdir, voxelsize, k, mul, cellsize, halo)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -198,4 +235,6 @@ def launch(world, backend, parts, tmpdir, voxelsize, k, mul, cellsize, halo=None
         numpy.save(os.path.join(indir, f"part{r}.npy"), p)
     mp.spawn(run_rank, args=(world, port, backend, indir, outdir, voxelsize, k, mul, cellsize, halo), nprocs=world, join=True)
     load = lambda name: [numpy.load(os.path.join(outdir, f"{name}{r}.npy")) for r in range(world)]  # noqa: E731
+    if backend == "lib":
+        return load("ds"), load("sor"), load("chain"), load("pertile"), load("tf"), load("tfmeta")
     return load("ds"), load("sor"), load("chain")

@@ -83,3 +83,69 @@ def test_slabs_nccl_one_gpu_per_rank(cw, orc, tmp_path):
     args = dict(voxelsize=0.005, k=30, mul=1.0, cellsize=0.002)
     dsn, sorn, chainn = runner.launch(world, "cuda-nccl", parts, str(tmp_path), port=29681, **args)
     check_against_single_gpu(cw, orc, parts, dsn, sorn, chainn, **args)
+
+
+# ---- the protocol inside the library (csrc/slab.cpp, NCCL) ------------------------------------------------------------------
+def test_library_slab_entry_points_with_one_rank(cw, orc):
+    """A communicator of size 1 needs no NCCL: the collective entry points reduce to the plain filters (same code path as
+    with several ranks, minus the transfers)."""
+    from cwipc_util_b200 import util
+    from parity_helpers import per_tile_check
+    pts = synthetic.camera_cloud(60000, seed=9)
+    pc = cw.cwipc_from_numpy_array(pts, 5)
+    pc._set_cellsize(0.002)
+    comm = util.cuda_comm(None, 1, 0)
+    for voxel in (0.01, -0.02):
+        want, cs, _, _ = orc.downsample(pts, voxel, 0.002)
+        got = comm.downsample(pc, voxel)
+        assert got.cellsize() == numpy.float32(cs) and got.timestamp() == 5
+        assert_points_close(got.get_numpy_array(), want, cs)
+    got = comm.remove_outliers(pc, 30, 1.0).get_numpy_array()
+    assert sor_group_check(pts, got, 0, orc.knn_mean_distances(pts, 30), 1.0) == len(got)
+    per_tile_check(orc, pts, comm.remove_outliers(pc, 30, 1.0, True).get_numpy_array(), 30, 1.0)
+    tf, off, tot = comm.tilefilter(pc, 4)
+    assert off == 0 and tot == tf.count() and numpy.array_equal(tf.get_numpy_array(), pts[pts["tile"] == 4])
+    comm.free()
+
+
+@pytest.mark.parametrize("voxelsize", [0.005, -0.01])
+def test_library_slabs_over_nccl(cw, orc, voxelsize, tmp_path):
+    """One GPU per rank, the library's own NCCL protocol: downsample / remove_outliers (whole cloud and per tile) /
+    tilefilter of the partitioned cloud against the single-GPU calls and the oracle.  Needs >= 2 GPUs."""
+    from parity_helpers import per_tile_check
+    if cw.cuda_device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    world = min(cw.cuda_device_count(), 4)
+    parts = make_parts(200000, world, seed=31)
+    args = dict(voxelsize=voxelsize, k=30, mul=1.0, cellsize=0.002)
+    dsn, sorn, chainn, pertile, tf, tfmeta = runner.launch(world, "lib", parts, str(tmp_path), port=29711, **args)
+    check_against_single_gpu(cw, orc, parts, dsn, sorn, chainn, **args)
+    whole = numpy.concatenate(parts)
+    # tilefilter: the pieces in rank order are the single-GPU result, and every rank knows where its piece sits
+    want = whole[whole["tile"] == 2]
+    assert numpy.array_equal(numpy.concatenate(tf), want)
+    off = 0
+    for r in range(world):
+        assert tfmeta[r][0] == off and tfmeta[r][1] == len(want)
+        off += len(tf[r])
+    # per tile: tile by tile (first-appearance order of the whole cloud), the ranks' pieces in rank order
+    _, first = numpy.unique(whole["tile"], return_index=True)
+    tiles = whole["tile"][numpy.sort(first)]
+    pos = [0] * world
+    rebuilt = []
+    for t in tiles:
+        grp_total = 0
+        for r in range(world):
+            grp_r = parts[r] if t == 0 else parts[r][parts[r]["tile"] == t]
+            # this rank's survivors of the group are a subsequence of its part of the group: walk it
+            piece = pertile[r][pos[r]:]
+            take, j = 0, 0
+            for row in grp_r:
+                if j < len(piece) and piece[j] == row:
+                    j += 1
+            take = j
+            rebuilt.append(piece[:take])
+            pos[r] += take
+            grp_total += take
+    assert all(pos[r] == len(pertile[r]) for r in range(world))
+    per_tile_check(orc, whole, numpy.concatenate(rebuilt), 30, 1.0)
