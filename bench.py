@@ -346,6 +346,68 @@ def measure_config4(cw, lib, peak):
     return out
 
 
+def measure_slab(cw, dist, torch, rank, world):
+    """BASELINE.json configs[3], the multi-GPU part: ONE 8M-point synthetic cloud partitioned into x-slabs over the ranks
+    (rank r holds the r-th x-quantile of the points, input order kept), filtered by the library's own NCCL protocol
+    (csrc/slab.cpp: cwipc_cuda_slab_downsample / _remove_outliers).  All ranks take part; device time of the slowest rank
+    (CUDA events on every rank's stream around the collective call, MAX over ranks), median of 3 after 1 warm-up."""
+    from cwipc_util_b200 import synthetic, util
+    lib = util.cwipc_util_dll_load()
+    n_req = 2828 * 2828
+    pts = synthetic.simulate_cameras(synthetic.synthetic_cloud(n_req), 4)
+    n_all = len(pts)
+    edges = np.quantile(pts["x"], np.linspace(0, 1, world + 1))
+    edges[0], edges[-1] = -np.inf, np.inf
+    part = pts[(pts["x"] >= edges[rank]) & (pts["x"] < edges[rank + 1])]
+    del pts
+    uid = None
+    if world > 1:
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t = torch.frombuffer(bytearray(util.cuda_comm.unique_id()), dtype=torch.uint8).clone().cuda()
+        dist.broadcast(t, src=0)
+        uid = bytes(t.cpu().numpy().tobytes())
+    comm = util.cuda_comm(uid, world, rank)
+    pc = cw.cwipc_from_numpy_array(part, 3)
+    pc._set_cellsize(synthetic.cellsize_of(n_req))
+
+    def timed(fn, reps=3):
+        times, res = [], None
+        for i in range(reps + 1):
+            lib.cwipc_cuda_flush_l2()
+            cw.cuda_synchronize()
+            dist_barrier(dist, torch)
+            tm = lib.cwipc_cuda_timer_create()
+            lib.cwipc_cuda_timer_start(tm)
+            res = fn()
+            lib.cwipc_cuda_timer_stop(tm)
+            cw.cuda_synchronize()
+            ms = dist_reduce(dist, torch, lib.cwipc_cuda_timer_elapsed_ms(tm), "MAX")
+            lib.cwipc_cuda_timer_destroy(tm)
+            if i >= 1:
+                times.append(ms)
+        return float(np.median(times)), res
+
+    out = {"what": "configs[3]: one 8M-point synthetic cloud as x-slabs over the ranks, library NCCL protocol (ncclSend/ncclRecv of device buffers), "
+                   "max over ranks of the CUDA-event time around the collective call", "points": n_all, "ranks": world, "rows": []}
+    ds005 = None
+    for vs in (0.002, 0.005, 0.01, 0.02, 0.05):
+        ms, d = timed(lambda: comm.downsample(pc, vs))
+        v = int(dist_reduce(dist, torch, d.count(), "SUM"))
+        out["rows"].append({"op": "downsample", "voxelsize": vs, "voxels": v, "ms": round(ms, 4), "Mpoints_per_s": round(n_all / ms / 1e3, 1)})
+        if vs == 0.005:
+            ds005 = d
+    ms, o = timed(lambda: comm.remove_outliers(ds005, K, STDDEV, False))
+    m_in = int(dist_reduce(dist, torch, ds005.count(), "SUM"))
+    out["rows"].append({"op": "remove_outliers of the downsample(0.005) result", "points": m_in, "kept": int(dist_reduce(dist, torch, o.count(), "SUM")), "ms": round(ms, 4),
+                        "Mpoints_per_s": round(m_in / ms / 1e3, 1)})
+    ms, o = timed(lambda: comm.remove_outliers(pc, K, STDDEV, False), reps=2)
+    out["rows"].append({"op": "remove_outliers of the raw cloud", "points": n_all, "kept": int(dist_reduce(dist, torch, o.count(), "SUM")), "ms": round(ms, 4),
+                        "Mpoints_per_s": round(n_all / ms / 1e3, 1)})
+    comm.free()
+    return out
+
+
 def run_ours(args):
     # stdout carries exactly ONE JSON line: everything else that libraries print there (e.g. NCCL's version banner)
     # is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
@@ -461,11 +523,14 @@ def run_ours(args):
     e2e_value = points_per_step * args.steps / (total_e2e_ms / 1e3) / 1e6
     pageable_value = frames_all * POINTS_PER_FRAME / (total_pageable_ms / 1e3) / 1e6
 
+    slab = measure_slab(cw, dist, torch, rank, world) if not args.skip_config4 else None   # every rank takes part
     if rank != 0:
-        dist_barrier(dist, torch)      # rank 0 times configs[3] meanwhile
+        dist_barrier(dist, torch)      # rank 0 times the single-GPU part of configs[3] meanwhile
         return
     peak, peak_src = measured_hbm_peak()
     config4 = measure_config4(cw, lib, peak) if not args.skip_config4 else None
+    if config4 is not None:
+        config4["slabs"] = slab
     dist_barrier(dist, torch)
     roofline = None
     if prof:
