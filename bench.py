@@ -647,6 +647,7 @@ def run_reference(args):
 
 
 def main():
+    global PASSES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -655,9 +656,11 @@ def main():
     ap.add_argument("--sequence-frames", type=int, default=SEQUENCE_FRAMES)
     ap.add_argument("--frames-per-gpu", type=int, default=0, help="diagnostics: this many frames on every GPU instead of its share of the sequence")
     ap.add_argument("--skip-config4", action="store_true", help="diagnostics: leave out the 8M-point configs[3] measurement")
+    ap.add_argument("--passes", type=int, default=PASSES, help="diagnostics: passes over the sequence per step (the contract value is 8)")
     ap.add_argument("--workers", type=int, default=0, help="host threads per GPU (0 = choose from the core count)")
     ap.add_argument("--cpu-frames", type=int, default=24)
     args = ap.parse_args()
+    PASSES = max(1, args.passes)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -3,9 +3,10 @@ set -x
 TAG=$1
 timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_${TAG}.log 2>&1; echo test_exit=$?; tail -3 gpurun_out/pytest_${TAG}.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; echo smoke_exit=$?; tail -1 gpurun_out/smoke_${TAG}.log
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo bench_exit=$?
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo bench_exit=$?
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>/dev/null; echo ref_exit=$?
-bash scripts/gpu_ncu.sh ${TAG} "knn_tile_kernel|knn_far_kernel|voxel_accumulate_kernel|radix_cluster_kernel|bbox_octree_kernel|voxel_emit_kernel|knn_layout_kernel|compact_kernel|stats_threshold_kernel|knn_keygen_kernel" 10 10
+bash scripts/gpu_ncu.sh ${TAG} "knn_tile_kernel|knn_far_kernel|voxel_stream_kernel|voxel_words_kernel|radix_cluster_kernel|voxel_emit_kernel|knn_layout_kernel|compact_kernel|stats_threshold_kernel|knn_keygen_kernel" 10 10
+python scripts/sass_summary.py > /dev/null
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_${TAG}.json")); r=d["roofline"]
