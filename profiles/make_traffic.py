@@ -6,6 +6,7 @@ the captured launches of dram__bytes_read.sum + dram__bytes_write.sum and of sms
     python profiles/make_traffic.py gpurun_out/prof_<tag>.ncu-rep <tag>
 """
 import csv
+import re
 import io
 import json
 import os
@@ -17,9 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def short(name):
-    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("cwcu::", "")
-    name = name.split("(")[0].replace("void ", "").strip()
-    return name.split("<")[0]
+    m = re.search(r"([A-Za-z_]\w*)\s*[<(]", name.replace("(anonymous namespace)", "anon"))
+    return m.group(1) if m else name
 
 
 def main():

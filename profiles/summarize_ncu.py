@@ -32,8 +32,13 @@ WANT = [
 
 
 def short(name):
-    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("cwcu::", "")
-    return name.split("(")[0].replace("void ", "").strip()
+    import re
+    flat = name.replace("(anonymous namespace)", "anon")
+    m = re.search(r"([A-Za-z_]\w*)\s*(<[^(]*>)?\s*\(", flat) or re.search(r"([A-Za-z_]\w*)\s*[<(]", flat)
+    if not m:
+        return name
+    targs = re.sub(r"\(int\)|\(bool\)|cwcu::|anon::|<unnamed>::", "", m.group(2) or "") if m.lastindex and m.lastindex >= 2 else ""
+    return m.group(1) + targs
 
 
 def to_bytes(v, unit):
