@@ -350,7 +350,8 @@ def measure_slab(cw, dist, torch, rank, world):
     """BASELINE.json configs[3], the multi-GPU part: ONE 8M-point synthetic cloud partitioned into x-slabs over the ranks
     (rank r holds the r-th x-quantile of the points, input order kept), filtered by the library's own NCCL protocol
     (csrc/slab.cpp: cwipc_cuda_slab_downsample / _remove_outliers).  All ranks take part; device time of the slowest rank
-    (CUDA events on every rank's stream around the collective call, MAX over ranks), median of 3 after 1 warm-up."""
+    (CUDA events on every rank's stream around the collective call, MAX over ranks), median of 3 after 1 warm-up.  The
+    downsample result is checked against ONE GPU on the concatenation of the parts: same records, bit for bit."""
     from cwipc_util_b200 import synthetic, util
     lib = util.cwipc_util_dll_load()
     n_req = 2828 * 2828
@@ -358,7 +359,9 @@ def measure_slab(cw, dist, torch, rank, world):
     n_all = len(pts)
     edges = np.quantile(pts["x"], np.linspace(0, 1, world + 1))
     edges[0], edges[-1] = -np.inf, np.inf
-    part = pts[(pts["x"] >= edges[rank]) & (pts["x"] < edges[rank + 1])]
+    slab_of = np.clip(np.searchsorted(edges, pts["x"], side="right") - 1, 0, world - 1)
+    part = pts[slab_of == rank]
+    whole = pts[np.argsort(slab_of, kind="stable")] if rank == 0 else None   # the parts in rank order
     del pts
     uid = None
     if world > 1:
@@ -388,6 +391,12 @@ def measure_slab(cw, dist, torch, rank, world):
                 times.append(ms)
         return float(np.median(times)), res
 
+    def digest(records):
+        """order-independent digest of 16-byte records: sum of mixed words modulo 2^61"""
+        w = np.ascontiguousarray(records).view(np.uint64).reshape(-1, 2)
+        h = (w[:, 0] * np.uint64(0x9E3779B97F4A7C15) ^ (w[:, 1] + np.uint64(0xC2B2AE3D27D4EB4F))) * np.uint64(0x165667B19E3779F9)
+        return int(h.sum(dtype=np.uint64)) & ((1 << 61) - 1) if len(h) else 0
+
     out = {"what": "configs[3]: one 8M-point synthetic cloud as x-slabs over the ranks, library NCCL protocol (ncclSend/ncclRecv of device buffers), "
                    "max over ranks of the CUDA-event time around the collective call", "points": n_all, "ranks": world, "rows": []}
     ds005 = None
@@ -397,6 +406,23 @@ def measure_slab(cw, dist, torch, rank, world):
         out["rows"].append({"op": "downsample", "voxelsize": vs, "voxels": v, "ms": round(ms, 4), "Mpoints_per_s": round(n_all / ms / 1e3, 1)})
         if vs == 0.005:
             ds005 = d
+    # bit-identity with one GPU: digests of the ranks' pieces add up (mod 2^61) to the digest of the single-GPU result
+    local = digest(ds005.get_numpy_array())
+    if dist is not None:
+        parts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(parts, torch.tensor([local], dtype=torch.int64, device="cuda"))
+        total = sum(int(p.item()) for p in parts) & ((1 << 61) - 1)
+    else:
+        total = local
+    if rank == 0:
+        whole_pc = cw.cwipc_from_numpy_array(whole, 3)
+        whole_pc._set_cellsize(synthetic.cellsize_of(n_req))
+        single = cw.cwipc_downsample(whole_pc, 0.005)
+        v_slabs = [r["voxels"] for r in out["rows"] if r["voxelsize"] == 0.005][0]
+        out["downsample_0.005_vs_one_gpu"] = {"voxels_one_gpu": single.count(), "voxels_slabs": v_slabs,
+                                              "records_identical": bool(single.count() == v_slabs and digest(single.get_numpy_array()) == total)}
+        single.free()
+        whole_pc.free()
     ms, o = timed(lambda: comm.remove_outliers(ds005, K, STDDEV, False))
     m_in = int(dist_reduce(dist, torch, ds005.count(), "SUM"))
     out["rows"].append({"op": "remove_outliers of the downsample(0.005) result", "points": m_in, "kept": int(dist_reduce(dist, torch, o.count(), "SUM")), "ms": round(ms, 4),

@@ -1452,7 +1452,7 @@ void table_size(size_t n, bool full, size_t &claim_limit, size_t &capacity) {
 } // namespace
 
 namespace {
-DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octree_split, const OctreeBox *external, int dev, cudaStream_t s) {
+DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octree_split, const OctreeBox *external, uint64_t total_points, int dev, cudaStream_t s) {
     DownsampleResult result;
     const size_t n = in->count;
     if (n == 0) {
@@ -1471,8 +1471,9 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
         result.error = "invalid voxel size " + std::to_string(cellsize);
         return result;
     }
-    // fixed-point scale of the voxel-relative offsets: |offset| <= cellsize (1 + eps), n of them must fit 2^62
-    int shift = 61 - bit_length((uint64_t)n);
+    // fixed-point scale of the voxel-relative offsets: |offset| <= cellsize (1 + eps), n of them must fit 2^62 (a part of a
+    // partitioned cloud uses the count of the whole cloud: same scale, same rounding as the one-GPU call)
+    int shift = 61 - bit_length(std::max((uint64_t)n, total_points));
     {
         int e;
         (void)std::frexp(cellsize, &e); // cellsize < 2^e
@@ -1669,7 +1670,7 @@ OctreeSeed no_seed() {
 } // namespace
 
 DownsampleResult downsample_points(const StoragePtr &in, float cellsize, bool octree_split, int dev, cudaStream_t s) {
-    return downsample_impl(in, cellsize, octree_split, nullptr, dev, s);
+    return downsample_impl(in, cellsize, octree_split, nullptr, 0, dev, s);
 }
 
 // Partitioned clouds: the octree box and the bounding box of the WHOLE cloud are supplied by the caller.
@@ -1689,7 +1690,7 @@ DownsampleResult downsample_points_planned(const StoragePtr &in, float cellsize,
         r.error = "planned downsample needs the octree state of the whole cloud";
         return r;
     }
-    return downsample_impl(in, cellsize, octree_split, &ob, dev, s);
+    return downsample_impl(in, cellsize, octree_split, &ob, state.points, dev, s);
 }
 
 // Continue the octree bounding-box replay over this cloud's points; also returns its bounding box.
@@ -1719,6 +1720,7 @@ void octree_replay(const cwipc_point *in, size_t n, float cellsize, OctreeState 
     }
     state.depth = ob.depth;
     state.valid = 1;
+    state.points += n;
 }
 
 void global_bbox(const cwipc_point *in, size_t n, float gmin[3], float gmax[3], int dev, cudaStream_t s) {

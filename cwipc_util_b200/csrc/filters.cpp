@@ -261,12 +261,14 @@ int cwipc_cuda_octree_replay(cwipc_pointcloud *pc, float cellsize, struct cwipc_
         memcpy(st.max, state->max, sizeof(st.max));
         st.depth = state->depth;
         st.valid = state->valid;
+        st.points = state->points;
         octree_replay(in->d_pts, in->count, cellsize, st, bounds, in->dev, s);
         in->release_after_read(s);
         memcpy(state->min, st.min, sizeof(st.min));
         memcpy(state->max, st.max, sizeof(st.max));
         state->depth = st.depth;
         state->valid = st.valid;
+        state->points = st.points;
         return 0;
     });
 }
@@ -287,6 +289,7 @@ cwipc_pointcloud *cwipc_cuda_downsample_planned(cwipc_pointcloud *pc, float voxe
         memcpy(st.max, state->max, sizeof(st.max));
         st.depth = state->depth;
         st.valid = state->valid;
+        st.points = state->points;
         DownsampleResult r;
         try {
             if (in->count == 0) {

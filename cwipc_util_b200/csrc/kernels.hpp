@@ -48,6 +48,9 @@ struct OctreeState {
     double min[3] = {0, 0, 0}, max[3] = {0, 0, 0};
     int depth = 0;
     int valid = 0;
+    // points inserted so far; the whole cloud's count fixes the fixed-point scale of the centroid sums, so every part of
+    // a partitioned cloud rounds exactly as the one-GPU call does
+    uint64_t points = 0;
 };
 void octree_replay(const cwipc_point *in, size_t n, float cellsize, OctreeState &state, float bounds[6], int dev, cudaStream_t s);
 DownsampleResult downsample_points_planned(const StoragePtr &in, float cellsize, bool octree_split, const OctreeState &state, const float bounds[6], int dev, cudaStream_t s);

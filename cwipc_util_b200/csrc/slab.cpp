@@ -10,8 +10,9 @@
 //
 // slab_downsample
 //   1. one all-gather of (cellsize, count, bounding box) per rank;
-//   2. octree box: PCL grows the octree's bounding box while points are inserted IN ORDER, so the box state travels
-//      rank 0 -> 1 -> ... (64 bytes per hop) and the final state is broadcast;
+//   2. octree box: PCL grows the octree's bounding box while points are inserted IN ORDER, so rank 0 replays its part and
+//      broadcasts the box state, then rank 1, ... until the box contains the whole cloud's bounding box (it doubles when
+//      it grows: usually after the first part);
 //   3. a voxel must be reduced by one rank: voxel columns floorf(x / cellsize) are assigned to ranks from the parts' own x
 //      minima, and every point that sits in a column owned by another rank is sent there (only the points of boundary
 //      voxels move when the parts are proper x-slabs);
@@ -215,9 +216,11 @@ StoragePtr slab_downsample_storage(const StoragePtr &in, float voxelsize, float 
     const std::vector<double> info = allgather_doubles(c, row, 8, s);
     float cs = std::fabs(voxelsize);
     bool any = false;
+    uint64_t total_points = 0;
     float gmin[3] = {INFINITY, INFINITY, INFINITY}, gmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int q = 0; q < G; q++) {
         cs = std::max(cs, (float)info[q * 8 + 0]); // ref: src/cwipc_filters.cpp:103-107 (the cloud's own cellsize wins when larger)
+        total_points += (uint64_t)info[q * 8 + 1];
         if (info[q * 8 + 1] > 0) {
             any = true;
             for (int a = 0; a < 3; a++) {
@@ -229,25 +232,30 @@ StoragePtr slab_downsample_storage(const StoragePtr &in, float voxelsize, float 
     *cellsize_out = cs;
     if (!any) return empty_storage(dev, s); // every part is empty: no leaves, an empty cloud (single-grid mode: the caller reports the reference's error)
 
-    // 2. octree box replay, rank by rank (the box grows with the points IN ORDER), then broadcast
+    // 2. octree box replay, rank by rank (the box grows with the points IN ORDER).  The box doubles every time it grows, so it
+    //    usually contains the whole cloud's bounding box after the first part or two: rank r replays its part and
+    //    broadcasts the state; as soon as the box contains the global bounding box no later point can move it, and the
+    //    chain stops (every rank takes the same decision from the same data).
     OctreeState state;
     if (octree) {
         Scratch wire(sizeof(OctreeState), s);
-        if (r > 0) {
-            NCCL_CHECK(nccl().Recv(wire.p, sizeof(OctreeState), NCCL_UINT8, r - 1, c->comm, s));
-            CWCU_CHECK(cudaMemcpyAsync(&state, wire.p, sizeof(OctreeState), cudaMemcpyDeviceToHost, s));
+        for (int q = 0; q < G; q++) {
+            if (q == r) {
+                float ignored[6];
+                octree_replay(in->d_pts, n, cs, state, ignored, dev, s);
+                CWCU_CHECK(cudaMemcpyAsync(wire.p, &state, sizeof(OctreeState), cudaMemcpyHostToDevice, s));
+            }
+            if (G > 1) {
+                NCCL_CHECK(nccl().Broadcast(wire.p, wire.p, sizeof(OctreeState), NCCL_UINT8, q, c->comm, s));
+                CWCU_CHECK(cudaMemcpyAsync(&state, wire.p, sizeof(OctreeState), cudaMemcpyDeviceToHost, s));
+            }
             stream_sync(s);
+            bool covers = state.valid != 0;
+            for (int a = 0; a < 3 && covers; a++) covers = (double)gmin[a] >= state.min[a] && (double)gmax[a] < state.max[a];
+            if (covers) break;
         }
-        float ignored[6];
-        octree_replay(in->d_pts, n, cs, state, ignored, dev, s);
-        CWCU_CHECK(cudaMemcpyAsync(wire.p, &state, sizeof(OctreeState), cudaMemcpyHostToDevice, s));
-        if (r < G - 1) NCCL_CHECK(nccl().Send(wire.p, sizeof(OctreeState), NCCL_UINT8, r + 1, c->comm, s));
-        if (G > 1) {
-            NCCL_CHECK(nccl().Broadcast(wire.p, wire.p, sizeof(OctreeState), NCCL_UINT8, G - 1, c->comm, s));
-            CWCU_CHECK(cudaMemcpyAsync(&state, wire.p, sizeof(OctreeState), cudaMemcpyDeviceToHost, s));
-        }
-        stream_sync(s);
     }
+    state.points = total_points; // fixes the fixed-point scale of the centroid sums: the same on every rank as in the one-GPU call
 
     // 3. voxel columns -> owners; boundary points move to the owner of their column
     const float inv = 1.0f / cs;

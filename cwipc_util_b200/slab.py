@@ -254,21 +254,21 @@ def slab_downsample(pc, voxelsize: float, comm: TorchComm, ops, timestamp: int =
     octree = not (voxelsize < 0)
 
     # 0. one collective for everything that is known locally: cellsize metadata, point count, bounding box
-    _, b = ops.replay(pc, 1.0, numpy.zeros(8))  # bounding box of this part (the octree state of this call is not used)
+    _, b = ops.replay(pc, 1.0, numpy.zeros(9))  # bounding box of this part (the octree state of this call is not used)
     info = comm.gather_rows([float(ops.cellsize(pc)), float(ops.count(pc))] + list(b))
     have = info[:, 1] > 0
     cs = numpy.float32(max(abs(voxelsize), float(info[:, 0].max())))  # ref: src/cwipc_filters.cpp:103-107
     if not have.any():  # every part is empty
-        return ops.downsample_planned(pc, voxelsize, numpy.zeros(8), numpy.zeros(6))
+        return ops.downsample_planned(pc, voxelsize, numpy.zeros(9), numpy.zeros(6))
     gmin = info[have, 2:5].min(axis=0)
     gmax = info[have, 5:8].max(axis=0)
     xmins = info[:, 2]
 
     # 1. octree box replay, rank by rank (the box grows with the points IN ORDER), then broadcast
-    state = numpy.zeros(8)
+    state = numpy.zeros(9)
     if octree:
         if r > 0:
-            state = comm.recv(8, r - 1)
+            state = comm.recv(9, r - 1)
         state, _ = ops.replay(pc, float(cs), state)
         if r < G - 1:
             comm.send(state, r + 1)
@@ -296,7 +296,9 @@ def slab_downsample(pc, voxelsize: float, comm: TorchComm, ops, timestamp: int =
     incoming = _exchange_points(comm, ops, outgoing, timestamp, float(ops.cellsize(pc)))
     mine = ops.join([keep] + incoming) if incoming else keep
 
-    # 3. the local reduction, with the whole cloud's octree box and bounding box
+    # 3. the local reduction, with the whole cloud's octree box, bounding box and point count (the count fixes the
+    #    fixed-point scale of the centroid sums: every part then rounds exactly as the one-GPU call does)
+    state[8] = float(info[:, 1].sum())
     return ops.downsample_planned(mine, voxelsize, state, numpy.concatenate([gmin, gmax]))
 
 
@@ -304,7 +306,7 @@ def slab_remove_outliers(pc, k: int, mul: float, comm: TorchComm, ops, halo: Opt
     """cwipc_remove_outliers(whole cloud, perTile=False) on the partitioned cloud; returns this rank's survivors."""
     G, r = comm.size, comm.rank
     n_local = ops.count(pc)
-    _, b = ops.replay(pc, 1.0, numpy.zeros(8))  # only the bounding box is used here
+    _, b = ops.replay(pc, 1.0, numpy.zeros(9))  # only the bounding box is used here
     info = comm.gather_rows([float(ops.cellsize(pc)), float(n_local), b[0] if n_local else numpy.inf, b[3] if n_local else -numpy.inf])
     counts = info[:, 1]
     ext = info[:, 2:4]

@@ -523,10 +523,10 @@ def downsample_keys(pc: cwipc_pointcloud_wrapper, voxelsize: float) -> numpy.nda
 # ---- partitioned clouds (one cloud over several GPUs; see slab.py) ----------------------------------
 class cwipc_cuda_octree_state(ctypes.Structure):
     """include/cwipc_util_cuda.h: struct cwipc_cuda_octree_state"""
-    _fields_ = [("min", ctypes.c_double * 3), ("max", ctypes.c_double * 3), ("depth", ctypes.c_int32), ("valid", ctypes.c_int32)]
+    _fields_ = [("min", ctypes.c_double * 3), ("max", ctypes.c_double * 3), ("depth", ctypes.c_int32), ("valid", ctypes.c_int32), ("points", ctypes.c_uint64)]
 
     def to_array(self) -> numpy.ndarray:
-        return numpy.array(list(self.min) + list(self.max) + [float(self.depth), float(self.valid)], numpy.float64)
+        return numpy.array(list(self.min) + list(self.max) + [float(self.depth), float(self.valid), float(self.points)], numpy.float64)
 
     @classmethod
     def from_array(cls, a) -> "cwipc_cuda_octree_state":
@@ -536,6 +536,7 @@ class cwipc_cuda_octree_state(ctypes.Structure):
             st.max[i] = float(a[3 + i])
         st.depth = int(a[6])
         st.valid = int(a[7])
+        st.points = int(a[8])
         return st
 
 

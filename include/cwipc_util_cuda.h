@@ -324,6 +324,8 @@ struct cwipc_cuda_octree_state { /* bounding box of pcl::octree::OctreePointClou
     double max[3];
     int32_t depth;
     int32_t valid; /* 0: nothing inserted yet */
+    uint64_t points; /* points inserted so far; cwipc_cuda_downsample_planned takes the scale of its fixed-point centroid
+                      * sums from the whole cloud's count, so that every part rounds exactly as the one-GPU call does */
 };
 /* Insert this cloud's points (in order) into the octree box `state` (in/out); bounds = min xyz, max xyz of the cloud. */
 _CWIPC_UTIL_EXPORT int cwipc_cuda_octree_replay(cwipc_pointcloud *pc, float cellsize, struct cwipc_cuda_octree_state *state, float bounds[6]);

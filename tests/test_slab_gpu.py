@@ -149,3 +149,31 @@ def test_library_slabs_over_nccl(cw, orc, voxelsize, tmp_path):
             grp_total += take
     assert all(pos[r] == len(pertile[r]) for r in range(world))
     per_tile_check(orc, whole, numpy.concatenate(rebuilt), 30, 1.0)
+
+
+def test_library_slabs_clean_synthetic_cloud_over_nccl(cw, orc, tmp_path):
+    """The clean synthetic cloud cut into x-quantile slabs (what bench.py's config4.slabs measures): the first point sits on
+    two coordinate planes, whole rings lie exactly on leaf faces, and the single-GPU call takes the fused pass while the
+    slabs take the planned one -- the records must still be the same, bit for bit."""
+    if cw.cuda_device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    world = min(cw.cuda_device_count(), 4)
+    pts = synthetic.simulate_cameras(synthetic.synthetic_cloud(640000), 4)
+    edges = numpy.quantile(pts["x"], numpy.linspace(0, 1, world + 1))
+    edges[0], edges[-1] = -numpy.inf, numpy.inf
+    slab_of = numpy.clip(numpy.searchsorted(edges, pts["x"], side="right") - 1, 0, world - 1)
+    parts = [pts[slab_of == r] for r in range(world)]
+    args = dict(voxelsize=0.005, k=30, mul=1.0, cellsize=float(synthetic.cellsize_of(640000)))
+    dsn, sorn, chainn, pertile, tf, tfmeta = runner.launch(world, "lib", parts, str(tmp_path), port=29731, **args)
+    whole = numpy.concatenate(parts)
+    pc = cw.cwipc_from_numpy_array(whole, 7)
+    pc._set_cellsize(args["cellsize"])
+    ds = cw.cwipc_downsample(pc, 0.005).get_numpy_array()
+    got = numpy.concatenate(dsn)
+    assert len(got) == len(ds)
+    a, b = sorted_records(got), sorted_records(ds)
+    only_slabs, only_single = numpy.setdiff1d(a, b), numpy.setdiff1d(b, a)
+    dt = got.dtype
+    assert len(only_slabs) == 0 and len(only_single) == 0, (only_slabs.view(dt), only_single.view(dt))
+    want, cs, _, _ = orc.downsample(whole, 0.005, args["cellsize"])
+    assert_points_close(ds, want, cs)
