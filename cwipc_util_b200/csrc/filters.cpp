@@ -204,6 +204,16 @@ cwipc_pointcloud *cwipc_remove_outliers(cwipc_pointcloud *pc, int kNeighbors, fl
         std::vector<int> tiles = tiles_in_first_appearance_order(in->d_pts, n, s);
         const bool has_zero = std::find(tiles.begin(), tiles.end(), 0) != tiles.end();
         auto out = std::make_shared<Storage>(dev, has_zero ? 2 * n : n, s);
+        static const bool sequential = getenv("CWIPC_CUDA_SOR_PER_TILE") && !strcmp(getenv("CWIPC_CUDA_SOR_PER_TILE"), "sequential"); // tests only
+        if (!has_zero && kNeighbors >= 1 && n > (size_t)kNeighbors && !sequential) {
+            // every group at once: one search index with the tile rank as a band of cells (outliers.cu)
+            out->count = remove_outliers_per_tile(in->d_pts, n, out->d_pts, tiles, kNeighbors, stddevMulThresh, spacing, bounds, dev, s);
+            inherit_bounds(*out, *in);
+            out->mark_ready();
+            return out;
+        }
+        // tile 0 among the values (the whole cloud is a group of its own, src/cwipc_filters.cpp:281-306) or fewer points
+        // than neighbours: group after group
         Scratch group(n * sizeof(cwipc_point), s);
         size_t total = 0;
         for (int tile : tiles) {

@@ -21,6 +21,11 @@ struct Predicate {
 // Stable compaction of in[0..n) by `pred` into out (capacity >= n).  Returns the number kept.
 size_t compact_points(const cwipc_point *in, size_t n, cwipc_point *out, const Predicate &pred, int dev, cudaStream_t s);
 
+// One link of a chain of compactions into the same `out`: keeps the points of `tile` with !(dist[i] > *threshold_dev),
+// writing from position *d_base (device word; 0 when null) and leaving base + kept in *d_total.  No read-back; n > 0.
+void compact_tile_group_chained(const cwipc_point *in, size_t n, cwipc_point *out, int tile, const float *dist, const double *threshold_dev, const uint32_t *d_base,
+                                uint32_t *d_total, cudaStream_t s);
+
 void tilemap_points(const cwipc_point *in, size_t n, cwipc_point *out, const uint8_t map[256], cudaStream_t s);
 void colormap_points(const cwipc_point *in, size_t n, cwipc_point *out, uint32_t clearBits, uint32_t setBits, cudaStream_t s);
 // min over i>=1 of |p_i - p_0| (float), 0 when n < 2.  ref: src/cwipc_util.cpp:173-204
@@ -64,6 +69,12 @@ void downsample_keys_to_host(const StoragePtr &in, float cellsize, bool octree_s
 // returns the number kept.  `hint_spacing` is the cloud's cellsize (0 if unknown).
 // `bounds` (min xyz, max xyz), when not null, is a box known to contain every point; it saves the bounding-box pass.
 size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out, int k, float stddev_mul, float hint_spacing, const float *bounds, int dev, cudaStream_t s);
+// cwipc_remove_outliers(perTile=true) in one pass (ref: src/cwipc_filters.cpp:238-261): `tiles` = the distinct, NON-ZERO tile
+// values in first-appearance order; one search index over the whole cloud with the tile rank as a band of cells, one kNN
+// launch, per-group statistics and thresholds on the device, the groups' survivors chained into `out` in `tiles` order.
+// Needs n > k.  group_kept (nullable) receives the survivors per group.
+size_t remove_outliers_per_tile(const cwipc_point *in, size_t n, cwipc_point *out, const std::vector<int> &tiles, int k, float stddev_mul, float hint_spacing, const float *bounds,
+                                int dev, cudaStream_t s);
 // First pass only: mean distance to the k nearest neighbours per point, original order, device array.
 // Only the first `nquery` points are queries (the rest are candidates only); d_kth, when not null, receives the
 // (k+1)-th smallest squared distance of every query.

@@ -47,7 +47,16 @@ struct GridParams {
     int gdim[3];   // cells per axis at level 0
     int idxbits;
     int top_level; // level at which the whole grid is one cell
+    // per-tile mode: the points of tile rank b live in the cells [b << band_bits, (b << band_bits) + xdim) along x, i.e. band
+    // b is exactly the level-`band_bits` node (b, 0, 0): one index, one launch, and no neighbour from another tile.
+    // bands == 1 otherwise (band_bits == top_level, xdim == gdim[0]).
+    int bands;
+    int band_bits;
+    int xdim;      // cells along x of ONE band (gdim[0] spans all bands)
     uint32_t table_off[KG_MAX_LEVELS]; // first entry of each level's table (entries are uint2)
+};
+struct BandLut {
+    uint8_t rank[256]; // tile value -> band
 };
 
 __host__ __device__ __forceinline__ int level_dim(int gdim, int level) { return ((gdim - 1) >> level) + 1; }
@@ -87,16 +96,17 @@ __device__ __forceinline__ float dist2(const Point16 &a, const Point16 &b) {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__global__ void __launch_bounds__(256) knn_keygen_kernel(const cwipc_point *__restrict__ pts, uint32_t n, GridParams gp, uint64_t *__restrict__ keys, uint2 *__restrict__ table,
-                                                          uint32_t table_words2) {
+__global__ void __launch_bounds__(256) knn_keygen_kernel(const cwipc_point *__restrict__ pts, uint32_t n, const __grid_constant__ GridParams gp, const __grid_constant__ BandLut lut,
+                                                          uint64_t *__restrict__ keys, uint2 *__restrict__ table, uint32_t table_words2) {
     // the table pyramid (and the far-query counter behind it) must start empty: cleared here, two launches before
     // knn_layout_kernel fills it, instead of by a separate memset
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < table_words2; i += gridDim.x * blockDim.x) table[i] = make_uint2(0u, 0u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Point16 p = ld_point_stream(pts, i);
-        const uint32_t cx = cell_of(cell_u(p.x, gp.gmin[0], gp.inv_h), gp.gdim[0]);
+        uint32_t cx = cell_of(cell_u(p.x, gp.gmin[0], gp.inv_h), gp.xdim);
         const uint32_t cy = cell_of(cell_u(p.y, gp.gmin[1], gp.inv_h), gp.gdim[1]);
         const uint32_t cz = cell_of(cell_u(p.z, gp.gmin[2], gp.inv_h), gp.gdim[2]);
+        if (gp.bands > 1) cx += (uint32_t)lut.rank[pt_tile(p)] << gp.band_bits;
         keys[i] = (morton3(cx, cy, cz) << gp.idxbits) | i;
     }
 }
@@ -282,6 +292,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
         const uint64_t code = word >> gp.idxbits;
         const Point16 q = spts16[qs];
         const float ux = cell_u(q.x, gp.gmin[0], gp.inv_h), uy = cell_u(q.y, gp.gmin[1], gp.inv_h), uz = cell_u(q.z, gp.gmin[2], gp.inv_h);
+        const uint32_t band = gp.bands > 1 ? (compact3(code >> 2) >> gp.band_bits) : 0u; // per-tile mode: the query's tile rank
 
         // groups: runs of lanes inside one level-KT_GROUP_LEVEL node (codes are non-decreasing along the lanes)
         const uint64_t node2 = code >> (3 * KT_GROUP_LEVEL);
@@ -297,8 +308,10 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
             const float lox = warp_min(live ? ux : INFINITY), loy = warp_min(live ? uy : INFINITY), loz = warp_min(live ? uz : INFINITY);
             const float hix = warp_max(live ? ux : -INFINITY), hiy = warp_max(live ? uy : -INFINITY), hiz = warp_max(live ? uz : -INFINITY);
             uint32_t nr = 0, total = 0;
+            // a group never spans two bands (band_bits >= KT_GROUP_LEVEL): its candidates are the cells of its own band only
+            const uint32_t xoff = gp.bands > 1 ? (__reduce_max_sync(FULL_MASK, live ? band : 0u) << gp.band_bits) : 0u;
             if (lox <= hix) { // the group has at least one live query (always, except for padding lanes)
-                const int cx0 = max((int)floorf(lox - rc), 0), cx1 = min((int)floorf(hix + rc), gp.gdim[0] - 1);
+                const int cx0 = max((int)floorf(lox - rc), 0), cx1 = min((int)floorf(hix + rc), gp.xdim - 1);
                 const int cy0 = max((int)floorf(loy - rc), 0), cy1 = min((int)floorf(hiy + rc), gp.gdim[1] - 1);
                 const int cz0 = max((int)floorf(loz - rc), 0), cz1 = min((int)floorf(hiz + rc), gp.gdim[2] - 1);
                 const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1, nbz = cz1 - cz0 + 1;
@@ -316,7 +329,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
                             const float dy = fmaxf(fmaxf((float)iy - hiy, loy - (float)(iy + 1)), 0.f);
                             const float dz = fmaxf(fmaxf((float)iz - hiz, loz - (float)(iz + 1)), 0.f);
                             const float dd = dx * dx + dy * dy + dz * dz;
-                            if (shell == 0 ? dd == 0.f : (dd > 0.f && dd <= rc2)) r = table[table_index(gp, 0, (uint32_t)ix, (uint32_t)iy, (uint32_t)iz)];
+                            if (shell == 0 ? dd == 0.f : (dd > 0.f && dd <= rc2)) r = table[table_index(gp, 0, (uint32_t)ix + xoff, (uint32_t)iy, (uint32_t)iz)];
                         }
                         const unsigned has = __ballot_sync(FULL_MASK, r.y > r.x);
                         if (r.y > r.x) ws.ranges[nr + __popc(has & lt)] = r;
@@ -488,7 +501,7 @@ __device__ __forceinline__ float list_absorb(float (&v)[KPL], float d2, bool pas
 // others are expanded together, eight lanes per node, one child per lane.
 template <int KPL>
 __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Point16 *__restrict__ spts16, uint32_t n, const GridParams &gp, int kk,
-                                        const uint2 *__restrict__ table, uint32_t leaf_points, FarNode *stack, float (&v)[KPL]) {
+                                        const uint2 *__restrict__ table, uint32_t leaf_points, FarNode *stack, float (&v)[KPL], uint32_t band = 0u) {
     const unsigned lane = lane_id();
     const float slack = 0.01f * gp.h;
 #pragma unroll
@@ -498,6 +511,10 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
     if (lane == 0) {
         FarNode root;
         root.pb = 0; root.pe = n; root.xy = 0; root.zl = (uint32_t)gp.top_level << 16; root.mind2 = 0.f;
+        if (gp.bands > 1) { // per-tile mode: the search never leaves the query's band, the level-band_bits node (band, 0, 0)
+            const uint2 r = table[table_index(gp, gp.band_bits, band, 0u, 0u)];
+            root.pb = r.x; root.pe = r.y; root.xy = band; root.zl = (uint32_t)gp.band_bits << 16;
+        }
         stack[0] = root;
     }
     int sp = 1;
@@ -540,7 +557,8 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
             r = table[table_index(gp, cl, chx, chy, chz)];
             if (r.y > r.x) {
                 const float pitch = ldexpf(gp.h, cl);
-                const float lo[3] = {gp.gmin[0] + (float)chx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
+                const uint32_t lx = chx - (band << (gp.band_bits - cl)); // x within the band (band == 0 outside the per-tile mode)
+                const float lo[3] = {gp.gmin[0] + (float)lx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
                 const float qq[3] = {q.x, q.y, q.z};
                 mind2 = 0.f;
 #pragma unroll
@@ -595,7 +613,8 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
     for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < nentries; ei += warps_total) {
         const FarEntry ent = far_list[ei];
         float v[KPL];
-        dfs_knn<KPL>(spts16[ent.q], ent.bound, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v);
+        const uint32_t band = gp.bands > 1 ? (compact3((sorted[ent.q] >> gp.idxbits) >> 2) >> gp.band_bits) : 0u;
+        dfs_knn<KPL>(spts16[ent.q], ent.bound, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v, band);
         // sum of sqrt over elements 1..k in ascending order (double), as the reference does
         double sq[KPL];
 #pragma unroll
@@ -743,6 +762,69 @@ __global__ void __launch_bounds__(ST_THREADS) stats_threshold_kernel(const float
     *threshold_out = mean + stddev_mul * sqrt(variance);
 }
 
+// The same for one tile group of a per-tile outlier removal: only the points whose tile is `tile` count; the group's
+// size is counted here too.  A group of at most k points has no statistics: threshold +inf, every point of it is kept.
+// partial: 3 * ST_BLOCKS doubles.
+__global__ void __launch_bounds__(ST_THREADS) stats_threshold_tile_kernel(const float *__restrict__ dist, const cwipc_point *__restrict__ pts, uint32_t n, uint32_t tile, int k,
+                                                                           double *partial, uint32_t *__restrict__ done_counter, double stddev_mul,
+                                                                           double *__restrict__ threshold_out, uint32_t *__restrict__ count_out) {
+    __shared__ double s_sum[ST_THREADS], s_sq[ST_THREADS], s_cnt[ST_THREADS];
+    __shared__ bool s_last;
+    double sum = 0.0, sq = 0.0;
+    uint32_t cnt = 0;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(pts);
+    for (uint32_t i = blockIdx.x * ST_THREADS + threadIdx.x; i < n; i += ST_BLOCKS * ST_THREADS) {
+        if ((__ldg(words + 4 * (size_t)i + 3) >> 24) != tile) continue;
+        const float d = dist[i];
+        sum += (double)d;
+        sq += (double)__fmul_rn(d, d);
+        cnt++;
+    }
+    s_sum[threadIdx.x] = sum;
+    s_sq[threadIdx.x] = sq;
+    s_cnt[threadIdx.x] = (double)cnt;
+    __syncthreads();
+    for (int o = ST_THREADS / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+            s_sq[threadIdx.x] += s_sq[threadIdx.x + o];
+            s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __stcg(partial + 3 * blockIdx.x, s_sum[0]);
+        __stcg(partial + 3 * blockIdx.x + 1, s_sq[0]);
+        __stcg(partial + 3 * blockIdx.x + 2, s_cnt[0]);
+        __threadfence();
+        const uint32_t ticket = atomicAdd(done_counter, 1u);
+        s_last = ticket == ST_BLOCKS - 1;
+        if (s_last) *done_counter = 0; // clean for the next call
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    s_sum[threadIdx.x] = __ldcg(partial + 3 * threadIdx.x);
+    s_sq[threadIdx.x] = __ldcg(partial + 3 * threadIdx.x + 1);
+    s_cnt[threadIdx.x] = __ldcg(partial + 3 * threadIdx.x + 2);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double tsum = 0.0, tsq = 0.0, dn = 0.0;
+    for (int b = 0; b < ST_BLOCKS; b++) {
+        tsum += s_sum[b];
+        tsq += s_sq[b];
+        dn += s_cnt[b];
+    }
+    *count_out = (uint32_t)dn;
+    if (dn <= (double)k) {
+        *threshold_out = __longlong_as_double(0x7ff0000000000000ll);
+        return;
+    }
+    const double mean = tsum / dn;
+    const double variance = (tsq - tsum * tsum / dn) / (dn - 1.0);
+    *threshold_out = mean + stddev_mul * sqrt(variance);
+}
+
 int bit_length(uint64_t v) {
     int b = 0;
     while (v) {
@@ -772,7 +854,7 @@ struct GridPlan {
 
 // Pitch ~ a fraction of the expected k-neighbour radius of a surface sampled at `spacing`; the main
 // pass covers rc pitches around each query group.  The dense tables bound the number of cells.
-GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, float hint_spacing) {
+GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, float hint_spacing, int bands = 1) {
     static const float pitch_factor = env_float("CWIPC_CUDA_KNN_PITCH", 1.0f, 0.05f, 20.f);
     static const float rc = env_float("CWIPC_CUDA_KNN_RC", 1.0f, 0.25f, 1.0f);
     GridPlan plan;
@@ -783,16 +865,20 @@ GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, 
     const double longest = std::max(ext[0], std::max(ext[1], ext[2]));
     if (!(spacing > 0.0)) {
         const double area = 2.0 * (ext[0] * ext[1] + ext[1] * ext[2] + ext[2] * ext[0]);
-        if (area > 0.0) spacing = std::sqrt(area / (double)n);
-        else if (longest > 0.0) spacing = longest / (double)n;
+        const double per_band = std::max(1.0, (double)n / (double)bands); // every tile group is a surface of its own
+        if (area > 0.0) spacing = std::sqrt(area / per_band);
+        else if (longest > 0.0) spacing = longest / per_band;
         else spacing = 1.0;
     }
     // expected k-neighbour radius on a surface: spacing * sqrt((k+1)/pi); reach of the main pass = rc * h
     double h = spacing * std::sqrt((double)(k + 1) / 3.14159265358979) * (double)pitch_factor;
     gp.idxbits = std::max(1, bit_length((uint64_t)n - 1));
-    const int max_axis_bits = std::min(13, (64 - gp.idxbits) / 3);
+    const int rank_bits = bands > 1 ? bit_length((uint64_t)bands - 1) : 0;
+    const int max_axis_bits = std::min(13, (64 - gp.idxbits) / 3) - rank_bits; // per-tile mode: the band number sits above the x cell bits
+    if (max_axis_bits < 2) throw CudaError{cudaErrorInvalidValue, "remove_outliers: too many points and tiles for one search index"};
     if (!(h > 0.0) || !std::isfinite(h)) h = 1.0;
-    const double cell_cap = (double)std::min<size_t>(std::max<size_t>(4 * n, (size_t)1 << 16), (size_t)1 << 25);
+    // the bands lie side by side along x, each padded to a power of two of cells (<= 2x on the longest axis)
+    const double cell_cap = (double)std::min<size_t>(std::max<size_t>(4 * n, (size_t)1 << 16), (size_t)1 << 25) / (bands > 1 ? 2.0 * (double)bands : 1.0);
     while (true) {
         const double cells = (std::floor(ext[0] / h) + 2) * (std::floor(ext[1] / h) + 2) * (std::floor(ext[2] / h) + 2);
         if (longest / h < (double)((1 << max_axis_bits) - 1) && cells <= cell_cap) break;
@@ -808,6 +894,14 @@ GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, 
         maxdim = std::max(maxdim, gp.gdim[a]);
     }
     gp.top_level = bit_length((uint64_t)maxdim - 1); // (gdim-1) >> top_level == 0 on every axis
+    gp.bands = std::max(1, bands);
+    gp.xdim = gp.gdim[0];
+    gp.band_bits = gp.top_level;
+    if (gp.bands > 1) {
+        gp.band_bits = std::max(gp.top_level, KT_GROUP_LEVEL); // a query group (level-KT_GROUP_LEVEL node) never spans two bands
+        gp.gdim[0] = ((gp.bands - 1) << gp.band_bits) + gp.xdim;
+        gp.top_level = gp.band_bits + rank_bits;
+    }
     size_t off = 0;
     for (int l = 0; l <= gp.top_level; l++) {
         gp.table_off[l] = (uint32_t)off;
@@ -850,7 +944,7 @@ struct KnnIndex {
     uint32_t *far_count = nullptr;
 };
 
-void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, int dev, cudaStream_t s) {
+void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, int dev, cudaStream_t s, const BandLut *lut = nullptr, int bands = 1) {
     float gmin[3], gmax[3];
     if (bounds) {
         for (int a = 0; a < 3; a++) {
@@ -862,7 +956,10 @@ void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hin
     }
     for (int a = 0; a < 3; a++)
         if (!std::isfinite(gmin[a]) || !std::isfinite(gmax[a])) throw CudaError{cudaErrorInvalidValue, "remove_outliers: pointcloud contains non-finite coordinates"};
-    const GridPlan plan = choose_grid(gmin, gmax, n, k, hint_spacing);
+    const GridPlan plan = choose_grid(gmin, gmax, n, k, hint_spacing, lut ? bands : 1);
+    BandLut band_lut;
+    if (lut) band_lut = *lut;
+    else memset(&band_lut, 0, sizeof(band_lut));
     ix.gp = plan.gp;
     const GridParams &gp = ix.gp;
     int axis_bits = 1;
@@ -876,7 +973,7 @@ void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hin
     ix.table = Scratch((plan.table_entries + 2) * sizeof(uint2), s);
     ix.far_count = reinterpret_cast<uint32_t *>(ix.table.as<uint2>() + plan.table_entries);
     launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] {
-        knn_keygen_kernel<<<stream_grid(std::max(n, plan.table_entries / 4), dev), 256, 0, s>>>(in, (uint32_t)n, gp, ix.keys_a.as<uint64_t>(), ix.table.as<uint2>(),
+        knn_keygen_kernel<<<stream_grid(std::max(n, plan.table_entries / 4), dev), 256, 0, s>>>(in, (uint32_t)n, gp, band_lut, ix.keys_a.as<uint64_t>(), ix.table.as<uint2>(),
                                                                                                  (uint32_t)(plan.table_entries + 2));
     });
     ix.sorted = radix_sort_u64(ix.keys_a.as<uint64_t>(), ix.keys_b.as<uint64_t>(), n, gp.idxbits, gp.idxbits + keybits, dev, s);
@@ -894,12 +991,14 @@ void check_k(int k, size_t n) {
 
 } // namespace
 
-void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s, float *d_kth, size_t nquery) {
+namespace {
+void knn_mean_distances_banded(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s, float *d_kth, size_t nquery,
+                               const BandLut *lut, int bands) {
     if (n == 0) return;
     check_k(k, n);
     if ((size_t)k >= n) throw CudaError{cudaErrorInvalidValue, "remove_outliers: needs more than kNeighbors points"};
     KnnIndex ix;
-    build_index(ix, in, n, k, hint_spacing, bounds, dev, s);
+    build_index(ix, in, n, k, hint_spacing, bounds, dev, s, lut, bands);
     // a query is queued at most once
     Scratch far_list((n + 64) * sizeof(FarEntry), s);
     const int kk = k + 1;
@@ -911,6 +1010,11 @@ void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spaci
     else if (kk <= 16) go(std::integral_constant<int, 16>{});
     else if (kk <= 32) go(std::integral_constant<int, 32>{});
     else go(std::integral_constant<int, 64>{});
+}
+} // namespace
+
+void knn_mean_distances(const cwipc_point *in, size_t n, int k, float hint_spacing, const float *bounds, float *d_dist, int dev, cudaStream_t s, float *d_kth, size_t nquery) {
+    knn_mean_distances_banded(in, n, k, hint_spacing, bounds, d_dist, dev, s, d_kth, nquery, nullptr, 1);
 }
 
 void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, const float *d_limits, size_t nq, int k, float hint_spacing, const float *bounds, float *d_lists, int dev,
@@ -1052,6 +1156,42 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
     p.dist = dist.as<float>();
     p.threshold_dev = d_thr;
     return compact_points(in, n, out, p, dev, s);
+}
+
+size_t remove_outliers_per_tile(const cwipc_point *in, size_t n, cwipc_point *out, const std::vector<int> &tiles, int k, float stddev_mul, float hint_spacing, const float *bounds,
+                                int dev, cudaStream_t s) {
+    const size_t T = tiles.size();
+    if (n == 0 || T == 0) return 0;
+    BandLut lut;
+    memset(&lut, 0, sizeof(lut));
+    for (size_t t = 0; t < T; t++) {
+        if (tiles[t] <= 0 || tiles[t] > 255 || T > 255) throw CudaError{cudaErrorInvalidValue, "remove_outliers_per_tile: tile values must be distinct and in 1..255"};
+        lut.rank[tiles[t]] = (uint8_t)t;
+    }
+    Scratch dist(n * sizeof(float), s);
+    knn_mean_distances_banded(in, n, k, hint_spacing, bounds, dist.as<float>(), dev, s, nullptr, (size_t)-1, &lut, (int)T);
+    // per group: statistics -> threshold (device), then its survivors behind those of the groups before it
+    Scratch partial(3 * ST_BLOCKS * sizeof(double), s);
+    Scratch thresholds(T * sizeof(double), s);
+    Scratch words((2 * T + 1) * sizeof(uint32_t), s); // totals[0..T] (running end positions in `out`), counts[0..T)
+    uint32_t *totals = words.as<uint32_t>(), *counts = totals + T + 1;
+    CWCU_CHECK(cudaMemsetAsync(totals, 0, sizeof(uint32_t), s));
+    uint32_t *done = static_cast<uint32_t *>(thread_zeroed(dev, ZW_HEADER_BYTES, s)) + 6; // word 6 of the zeroed workspace header
+    for (size_t t = 0; t < T; t++) {
+        launch("stats_kernel", s, 8 * (size_t)n, [&] {
+            stats_threshold_tile_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), in, (uint32_t)n, (uint32_t)tiles[t], k, partial.as<double>(), done, (double)stddev_mul,
+                                                                         thresholds.as<double>() + t, counts + t);
+        });
+        compact_tile_group_chained(in, n, out, tiles[t], dist.as<float>(), thresholds.as<double>() + t, totals + t, totals + t + 1, s);
+    }
+    uint32_t *h = static_cast<uint32_t *>(thread_pinned((2 * T + 1) * sizeof(uint32_t)));
+    CWCU_CHECK(cudaMemcpyAsync(h, words.p, (2 * T + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    stream_sync(s);
+    for (size_t t = 0; t < T; t++)
+        if (h[T + 1 + t] <= (uint32_t)k)
+            log(CWIPC_LOG_LEVEL_WARNING, "cwipc_remove_outliers", "fewer points than kNeighbors+1 (" + std::to_string(h[T + 1 + t]) + " <= " + std::to_string(k) + "): keeping all points");
+    profile_add_bytes("compact_kernel", 16 * (size_t)h[T]);
+    return h[T];
 }
 
 } // namespace cwcu

@@ -46,9 +46,19 @@ struct DistPredDev { // threshold produced on the device by stats_threshold_kern
     __device__ __forceinline__ bool operator()(const Point16 &, uint32_t i) const { return !((double)dist[i] > __ldg(threshold)); }
 };
 
+struct DistTilePredDev { // one tile group of a per-tile outlier removal: the group's points that pass the group's threshold
+    const float *dist;
+    const double *threshold;
+    uint32_t tile;
+    __device__ __forceinline__ bool operator()(const Point16 &p, uint32_t i) const { return pt_tile(p) == tile && !((double)dist[i] > __ldg(threshold)); }
+};
+
+// d_base (nullable): device word holding the position in `out` at which this launch starts writing (the total of the
+// launch before it in a chain); d_total receives base + number kept.
 template <class Pred>
 __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *__restrict__ in, uint32_t n, cwipc_point *__restrict__ out, Pred pred,
-                                                              uint32_t *__restrict__ ticket, uint64_t *status, uint32_t *__restrict__ d_total, uint32_t *done_counter) {
+                                                              uint32_t *__restrict__ ticket, uint64_t *status, uint32_t *__restrict__ d_total, uint32_t *done_counter,
+                                                              const uint32_t *__restrict__ d_base) {
     __shared__ int s_tile;
     __shared__ uint32_t s_warp_total[CP_THREADS / 32];
     __shared__ uint32_t s_tile_excl;
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *
         block_total += t;
     }
     if (warp == 0) {
-        const uint32_t excl = lookback_exclusive(status, tile, block_total);
+        const uint32_t excl = lookback_exclusive(status, tile, block_total) + (d_base ? __ldcg(d_base) : 0u);
         if (lane == 0) {
             s_tile_excl = excl;
             if (tile_base + CP_TILE >= n) *d_total = excl + block_total;
@@ -123,8 +133,11 @@ __global__ void __launch_bounds__(CP_THREADS) compact_kernel(const cwipc_point *
     }
 }
 
+// chain_total != nullptr: the launch is one link of a chain -- it starts at *chain_base (0 when null), leaves base + kept in
+// *chain_total (device memory) and nothing is read back (returns 0); n > 0.
 template <class Pred>
-size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred, cudaStream_t s, size_t pred_bytes = 16) {
+size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred, cudaStream_t s, size_t pred_bytes = 16, const uint32_t *chain_base = nullptr,
+                   uint32_t *chain_total = nullptr) {
     if (n == 0) return 0;
     const size_t ntiles = div_up(n, CP_TILE);
     // [ticket u32 | total u32 | done u32 | pad | status u64 * ntiles]: in the zeroed workspace (cleared by the kernel itself)
@@ -144,11 +157,12 @@ size_t run_compact(const cwipc_point *in, size_t n, cwipc_point *out, Pred pred,
         words = scratch.as<uint32_t>();
     }
     uint32_t *ticket = words;
-    uint32_t *d_total = words + 1;
+    uint32_t *d_total = chain_total ? chain_total : words + 1;
     uint64_t *status = reinterpret_cast<uint64_t *>(words + 4);
     launch("compact_kernel", s, pred_bytes * (size_t)n, [&] {
-        compact_kernel<Pred><<<(unsigned)ntiles, CP_THREADS, 0, s>>>(in, (uint32_t)n, out, pred, ticket, status, d_total, done);
+        compact_kernel<Pred><<<(unsigned)ntiles, CP_THREADS, 0, s>>>(in, (uint32_t)n, out, pred, ticket, status, d_total, done, chain_base);
     });
+    if (chain_total) return 0;
     uint32_t *h = static_cast<uint32_t *>(thread_pinned(sizeof(uint32_t)));
     CWCU_CHECK(cudaMemcpyAsync(h, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     stream_sync(s);
@@ -235,6 +249,11 @@ size_t compact_points(const cwipc_point *in, size_t n, cwipc_point *out, const P
         return run_compact(in, n, out, DistPred{pred.dist, pred.threshold}, s, 20);
     }
     return 0;
+}
+
+void compact_tile_group_chained(const cwipc_point *in, size_t n, cwipc_point *out, int tile, const float *dist, const double *threshold_dev, const uint32_t *d_base,
+                                uint32_t *d_total, cudaStream_t s) {
+    (void)run_compact(in, n, out, DistTilePredDev{dist, threshold_dev, (uint32_t)tile}, s, 20, d_base, d_total);
 }
 
 static int device_of_stream_guard() {

@@ -56,6 +56,40 @@ def test_per_tile_with_tile_zero_and_small_groups(cw, orc):
     per_tile_check(orc, pts, got, 30, 1.0)
 
 
+def test_per_tile_many_tiles_and_small_groups_in_one_pass(cw, orc):
+    """No tile 0: every group goes through ONE search index (tile rank = a band of cells).  37 tile values of very
+    different sizes, two groups with fewer points than neighbours, groups interleaved point by point."""
+    pts = synthetic.camera_cloud(120000, seed=21)
+    idx = np.arange(len(pts))
+    pts["tile"] = 1 + (idx * 7919 % 37)          # 37 interleaved groups ...
+    pts["tile"][idx % 5 == 0] = 200              # ... one much larger than the others
+    pts["tile"][100:110] = 77                    # fewer points than neighbours: kept as they are
+    pts["tile"][5000] = 78
+    got = download(cw.cwipc_remove_outliers(upload(cw, pts), 30, 1.0, True))
+    assert 0 < len(got) < len(pts)
+    per_tile_check(orc, pts, got, 30, 1.0)
+    # without a cellsize hint the pitch comes from the bounding box; other k / multiplier
+    got = download(cw.cwipc_remove_outliers(upload(cw, pts, cellsize=0.0), 8, 2.0, True))
+    per_tile_check(orc, pts, got, 8, 2.0)
+
+
+def test_per_tile_one_pass_equals_group_after_group(cw):
+    """CWIPC_CUDA_SOR_PER_TILE=sequential (tests only) runs the groups one after the other, each with an index of its
+    own: same bytes."""
+    import subprocess
+    pts = synthetic.camera_cloud(300000, seed=22)
+    got = download(cw.cwipc_remove_outliers(upload(cw, pts, cellsize=synthetic.cellsize_of(len(pts))), 30, 1.0, True))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from cwipc_util_b200 import synthetic, util as cw\n"
+            "pts = synthetic.camera_cloud(300000, seed=22)\n"
+            "pc = cw.cwipc_from_numpy_array(pts, 1); pc._set_cellsize(synthetic.cellsize_of(len(pts)))\n"
+            "out = cw.cwipc_remove_outliers(pc, 30, 1.0, True).get_numpy_array()\n"
+            "sys.stdout.buffer.write(out.tobytes())" % REPO)
+    env = dict(os.environ, CWIPC_CUDA_SOR_PER_TILE="sequential")
+    raw = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, check=True, timeout=600).stdout
+    want = np.frombuffer(raw, DT)
+    assert np.array_equal(got, want)
+
+
 # ---- configs[3] ------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def cloud8m():
