@@ -44,6 +44,9 @@ struct GridParams {
     float inv_h;   // 1 / cell pitch
     float h;       // cell pitch
     float rc;      // cover radius of the main pass, in cell pitches (<= 1)
+    float rc_far;  // open queries whose (k+1)-th distance so far is within this many pitches get a second scan (knn_second_kernel)
+    int second_min; // ... when at least this many of them share a query group
+    int second_max; // ... and the scan lists at most this many candidates per open query
     int gdim[3];   // cells per axis at level 0
     int idxbits;
     int top_level; // level at which the whole grid is one cell
@@ -243,6 +246,9 @@ struct __align__(128) KnnWarpSmem {
     float buf[KT_BUF][32];          // 2048 B
     uint2 ranges[KT_MAXR];          // 512 B
     uint64_t mbar[KT_STAGES];
+    float pbox[7];                  // knn_second_kernel: box and radius (cell units) of the group being listed
+    uint32_t xoff;                  //   first cell (x) of the group's band (per-tile mode)
+    uint32_t cursor;                //   next cell of the box to be listed
 };
 
 __device__ __forceinline__ float warp_min(float v) {
@@ -406,22 +412,254 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
                 if (lane == 0 && chunk + 2 < nchunks) fill(st, chunk + 2);
             }
 
-            if (!live) continue;
             const float worst = best[KCAP - 1];
-            if (gp.top_level == 0 || worst <= reach2) {
-                double sum = 0.0;
-#pragma unroll
-                for (int j = 0; j < KCAP; j++)
-                    if (j > extra) sum += sqrt((double)best[j]); // j == extra is the query itself (distance 0)
-                dist_out[(size_t)(word & idxmask)] = (float)(sum / (double)k);
-                if (kth_out) kth_out[(size_t)(word & idxmask)] = worst;
-            } else {
-                const uint32_t slot = atomicAdd(far_count, 1u);
-                FarEntry e;
-                e.q = qi;
-                e.bound = worst;
-                far_list[slot] = e;
+            const bool done = live && (gp.top_level == 0 || worst <= reach2);
+            // the group's open queries are queued side by side (one atomic per group): knn_second_kernel finds them together again
+            const unsigned fm = __ballot_sync(FULL_MASK, live && !done);
+            if (fm) {
+                uint32_t slot = 0;
+                if (lane == (unsigned)(__ffs(fm) - 1)) slot = atomicAdd(far_count, (uint32_t)__popc(fm));
+                slot = __shfl_sync(FULL_MASK, slot, __ffs(fm) - 1);
+                if (live && !done) {
+                    FarEntry e;
+                    e.q = qi;
+                    e.bound = worst;
+                    far_list[slot + __popc(fm & lt)] = e;
+                }
             }
+            if (!done) continue;
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < KCAP; j++)
+                if (j > extra) sum += sqrt((double)best[j]); // j == extra is the query itself (distance 0)
+            dist_out[(size_t)(word & idxmask)] = (float)(sum / (double)k);
+            if (kth_out) kth_out[(size_t)(word & idxmask)] = worst;
+        }
+        __syncwarp();
+    }
+}
+
+
+// ---- second scan: the open queries whose neighbours are known to lie within rc_far pitches --------------
+// An open query leaves the main pass with a valid bound on its (k+1)-th distance.  Where many queries are open (raw,
+// noisy clouds: a thick shell rather than a surface) they sit side by side in the queue, group by group, and scanning
+// the cells within the bound of their common box once more -- 32 queries per candidate load, as in the main pass --
+// costs a fraction of one tree search per query.  Same lanes-are-queries scheme as knn_tile_kernel; the box can be
+// larger than the range list, which is then filled and scanned piece by piece.  Queries whose bound exceeds rc_far
+// pitches (isolated points) move on to far_list2 for knn_far_kernel.
+template <int KCAP>
+__global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_second_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, GridParams gp, int kk, int k,
+                                                                 const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out,
+                                                                 const FarEntry *__restrict__ far_list, const uint32_t *__restrict__ far_count, uint32_t second_from,
+                                                                 FarEntry *__restrict__ far_list2, uint32_t *__restrict__ far_count2) {
+    extern __shared__ __align__(128) unsigned char knn_smem_raw[];
+    constexpr int B = KCAP < KT_BUF ? KCAP : KT_BUF;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    KnnWarpSmem &ws = reinterpret_cast<KnnWarpSmem *>(knn_smem_raw)[warp];
+    const unsigned lt = lanemask_lt();
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < KT_STAGES; st++) mbar_init(&ws.mbar[st], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase_bits = 0;
+
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint64_t idxmask = (1ull << gp.idxbits) - 1ull;
+    const int extra = KCAP - kk;
+    const uint32_t nent = *far_count;
+    // Few open queries are isolated points, which the tree search serves best; many (one query in eight or more: a dense,
+    // noisy shell rather than a surface) are each other's neighbours, and that is what this scan is for.
+    if (nent < second_from) return;
+    const uint32_t nitems = (nent + 31u) >> 5;
+    const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
+
+    for (uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += warps_total) {
+        const uint32_t ei = item * 32u + lane;
+        const bool valid = ei < nent;
+        const FarEntry ent = far_list[valid ? ei : nent - 1u];
+        const uint64_t word = sorted[ent.q];
+        const uint64_t code = word >> gp.idxbits;
+        const Point16 q = spts16[ent.q];
+        // radius in cell units that holds every neighbour of the query (0.02 pitch covers the rounding of cell_u)
+        const float need = sqrtf(ent.bound) * gp.inv_h * 1.000001f + 0.02f;
+        // groups: runs of lanes inside one level-KT_GROUP_LEVEL node (what the main pass queued together)
+        const uint64_t node2 = code >> (3 * KT_GROUP_LEVEL);
+        bool active = valid && need <= gp.rc_far; // (a bound of +inf or NaN is not)
+        {
+            // a scan serves every open query of the group at once; for a few lonely ones the tree search is cheaper
+            const unsigned peers = __match_any_sync(FULL_MASK, node2) & __ballot_sync(FULL_MASK, active);
+            active = active && __popc(peers) >= gp.second_min;
+        }
+        {
+            const unsigned fm = __ballot_sync(FULL_MASK, valid && !active);
+            if (fm) {
+                uint32_t slot = 0;
+                if (lane == (unsigned)(__ffs(fm) - 1)) slot = atomicAdd(far_count2, (uint32_t)__popc(fm));
+                slot = __shfl_sync(FULL_MASK, slot, __ffs(fm) - 1);
+                if (valid && !active) far_list2[slot + __popc(fm & lt)] = ent;
+            }
+        }
+        if (!__any_sync(FULL_MASK, active)) continue;
+
+        const uint64_t prev_node2 = __shfl_up_sync(FULL_MASK, node2, 1);
+        const unsigned heads = __ballot_sync(FULL_MASK, (lane == 0) || (node2 != prev_node2));
+        const int m = __popc(heads);
+        const int ord = __popc(heads & (lt | (1u << lane))) - 1;
+
+        for (int g = 0; g < m; g++) {
+            const bool live = active && ord == g;
+            if (!__any_sync(FULL_MASK, live)) continue;
+            {
+                const float ux = cell_u(q.x, gp.gmin[0], gp.inv_h), uy = cell_u(q.y, gp.gmin[1], gp.inv_h), uz = cell_u(q.z, gp.gmin[2], gp.inv_h);
+                const float lx = warp_min(live ? ux : INFINITY), ly = warp_min(live ? uy : INFINITY), lz = warp_min(live ? uz : INFINITY);
+                const float hx = warp_max(live ? ux : -INFINITY), hy = warp_max(live ? uy : -INFINITY), hz = warp_max(live ? uz : -INFINITY);
+                const float pr = warp_max(live ? need : 0.f);
+                const uint32_t band = gp.bands > 1 ? __reduce_max_sync(FULL_MASK, live ? (compact3(code >> 2) >> gp.band_bits) : 0u) : 0u;
+                if (lane == 0) {
+                    ws.pbox[0] = lx; ws.pbox[1] = ly; ws.pbox[2] = lz;
+                    ws.pbox[3] = hx; ws.pbox[4] = hy; ws.pbox[5] = hz;
+                    ws.pbox[6] = pr;
+                    ws.xoff = band << gp.band_bits;
+                    ws.cursor = 0u;
+                }
+            }
+            __syncwarp();
+
+            float best[KCAP];
+#pragma unroll
+            for (int j = 0; j < KCAP; j++) best[j] = (j < extra) ? -INFINITY : INFINITY;
+            // everything up to the bound (inclusive) is collected: at least kk points are
+            float tau = live ? __uint_as_float(__float_as_uint(ent.bound) + 1u) : -INFINITY;
+            uint32_t bcnt = 0;
+            bool first = true, rejected = false;
+
+            while (true) {
+                // ---- list cell ranges from the cursor on, until the list is full or the box is complete ----
+                uint32_t total = 0;
+                bool box_done;
+                {
+                    const float plox = ws.pbox[0], ploy = ws.pbox[1], ploz = ws.pbox[2], phix = ws.pbox[3], phiy = ws.pbox[4], phiz = ws.pbox[5], prad = ws.pbox[6];
+                    const uint32_t xoff = ws.xoff;
+                    uint32_t nr = 0, cursor = ws.cursor;
+                    const int cx0 = max((int)floorf(plox - prad), 0), cx1 = min((int)floorf(phix + prad), gp.xdim - 1);
+                    const int cy0 = max((int)floorf(ploy - prad), 0), cy1 = min((int)floorf(phiy + prad), gp.gdim[1] - 1);
+                    const int cz0 = max((int)floorf(ploz - prad), 0), cz1 = min((int)floorf(phiz + prad), gp.gdim[2] - 1);
+                    const int nbx = cx1 - cx0 + 1, nby = cy1 - cy0 + 1, nbz = cz1 - cz0 + 1;
+                    const uint32_t nb = (uint32_t)max(nbx * nby * nbz, 0);
+                    const float prad2 = prad * prad;
+                    while (cursor < nb) {
+                        const int t = (int)(cursor + lane);
+                        uint2 r = make_uint2(0u, 0u);
+                        if (t < (int)nb) {
+                            const int ix = cx0 + t % nbx, iy = cy0 + (t / nbx) % nby, iz = cz0 + t / (nbx * nby);
+                            const float dx = fmaxf(fmaxf((float)ix - phix, plox - (float)(ix + 1)), 0.f);
+                            const float dy = fmaxf(fmaxf((float)iy - phiy, ploy - (float)(iy + 1)), 0.f);
+                            const float dz = fmaxf(fmaxf((float)iz - phiz, ploz - (float)(iz + 1)), 0.f);
+                            if (dx * dx + dy * dy + dz * dz <= prad2) r = table[table_index(gp, 0, (uint32_t)ix + xoff, (uint32_t)iy, (uint32_t)iz)];
+                        }
+                        const unsigned has = __ballot_sync(FULL_MASK, r.y > r.x);
+                        if (r.y > r.x) ws.ranges[nr + __popc(has & lt)] = r;
+                        nr += __popc(has);
+                        total += warp_sum(r.y - r.x);
+                        cursor += 32u;
+                        if (nr > (uint32_t)(KT_MAXR - 32)) break; // the list is full: scan what it holds, then go on
+                    }
+                    box_done = cursor >= nb;
+                    __syncwarp();
+                    if (lane == 0) ws.cursor = cursor;
+                }
+                __syncwarp();
+                if (first) {
+                    // The scan costs `total` distance evaluations per lane whatever the number of open queries it serves; the
+                    // tree search costs a few thousand instructions per query.  Scattered open queries (isolated points far
+                    // from the surface: a large box, few of them) are left to the tree search.
+                    first = false;
+                    const uint32_t nlive = (uint32_t)__popc(__ballot_sync(FULL_MASK, live));
+                    if (!box_done || total > nlive * (uint32_t)gp.second_max) {
+                        rejected = true;
+                        break;
+                    }
+                }
+
+                // ---- stream the listed candidates through the ring (as knn_tile_kernel does) ----
+                const uint32_t nchunks = (total + KT_CH - 1) / KT_CH;
+                uint32_t ri = 0, roff = 0; // producer cursor (lane 0)
+                auto fill = [&](int st, uint32_t chunk) {
+                    const uint32_t cnt = min((uint32_t)KT_CH, total - chunk * KT_CH);
+                    mbar_arrive_expect_tx(&ws.mbar[st], cnt * 16u);
+                    uint32_t filled = 0;
+                    while (filled < cnt) {
+                        const uint2 r = ws.ranges[ri];
+                        const uint32_t len = r.y - r.x;
+                        const uint32_t take = min(len - roff, cnt - filled);
+                        bulk_g2s(&ws.cand[st][filled], spts16 + r.x + roff, take * 16u, &ws.mbar[st]);
+                        filled += take;
+                        roff += take;
+                        if (roff == len) {
+                            ri++;
+                            roff = 0;
+                        }
+                    }
+                };
+                if (lane == 0 && nchunks > 0) {
+                    fill(0, 0);
+                    if (nchunks > 1) fill(1, 1);
+                }
+                for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
+                    const int st = (int)(chunk & 1u);
+                    mbar_wait(&ws.mbar[st], (phase_bits >> st) & 1u);
+                    phase_bits ^= 1u << st;
+                    const uint32_t cnt = min((uint32_t)KT_CH, total - chunk * KT_CH);
+                    const bool last_chunk = chunk + 1 == nchunks;
+                    for (uint32_t c = 0; c < cnt; c += 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (c + u < cnt) {
+                                const Point16 cand = ws.cand[st][c + u];
+                                const float d2 = dist2(q, cand);
+                                if (d2 < tau) {
+                                    ws.buf[bcnt][lane] = d2;
+                                    bcnt++;
+                                }
+                            }
+                        }
+                        const bool finish = last_chunk && c + 4 >= cnt;
+                        if (finish || __any_sync(FULL_MASK, bcnt > (uint32_t)(B - 4))) {
+                            float s[B];
+#pragma unroll
+                            for (int j = 0; j < B; j++) s[j] = ((uint32_t)j < bcnt) ? ws.buf[j][lane] : INFINITY;
+                            bitonic_sort_asc<B>(s);
+#pragma unroll
+                            for (int j = 0; j < B; j++) best[KCAP - 1 - j] = fminf(best[KCAP - 1 - j], s[j]);
+                            bitonic_merge_asc<KCAP>(best);
+                            bcnt = 0;
+                            // the bound stays in force until kk distances are in (best[KCAP-1] is +inf until then)
+                            if (live) tau = fminf(tau, best[KCAP - 1]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0 && chunk + 2 < nchunks) fill(st, chunk + 2);
+                }
+                if (box_done) break;
+            }
+            if (rejected) {
+                const unsigned fm = __ballot_sync(FULL_MASK, live);
+                uint32_t slot = 0;
+                if (lane == (unsigned)(__ffs(fm) - 1)) slot = atomicAdd(far_count2, (uint32_t)__popc(fm));
+                slot = __shfl_sync(FULL_MASK, slot, __ffs(fm) - 1);
+                if (live) far_list2[slot + __popc(fm & lt)] = ent;
+                continue;
+            }
+
+            if (!live) continue;
+            double sum = 0.0;
+#pragma unroll
+            for (int j = 0; j < KCAP; j++)
+                if (j > extra) sum += sqrt((double)best[j]);
+            dist_out[(size_t)(word & idxmask)] = (float)(sum / (double)k);
+            if (kth_out) kth_out[(size_t)(word & idxmask)] = best[KCAP - 1];
         }
         __syncwarp();
     }
@@ -603,9 +841,16 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
 template <int KPL>
 __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out,
-                                                              const FarEntry *__restrict__ far_list, const uint32_t *__restrict__ far_count, uint32_t leaf_points) {
+                                                              const FarEntry *__restrict__ far_list, const uint32_t *__restrict__ far_count, uint32_t second_from,
+                                                              uint32_t leaf_points) {
     __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    // when the second scan ran (the main pass queued at least second_from queries) the list it passed on is the one to
+    // take: it lies (n + 64) entries behind the main pass's, its counter one word behind
+    if (far_count[0] >= second_from) {
+        far_list += (size_t)n + 64;
+        far_count += 1;
+    }
     const uint32_t nentries = *far_count;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint64_t idxmask = (1ull << gp.idxbits) - 1ull;
@@ -857,6 +1102,7 @@ struct GridPlan {
 GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, float hint_spacing, int bands = 1) {
     static const float pitch_factor = env_float("CWIPC_CUDA_KNN_PITCH", 1.0f, 0.05f, 20.f);
     static const float rc = env_float("CWIPC_CUDA_KNN_RC", 1.0f, 0.25f, 1.0f);
+    static const float rc_far = env_float("CWIPC_CUDA_KNN_RC_FAR", 2.0f, 0.f, 8.f); // 0: no second scan
     GridPlan plan;
     GridParams &gp = plan.gp;
     memset(&gp, 0, sizeof(gp));
@@ -887,6 +1133,9 @@ GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, 
     gp.h = (float)h;
     gp.inv_h = 1.0f / gp.h;
     gp.rc = rc;
+    gp.rc_far = rc_far;
+    gp.second_min = (int)env_float("CWIPC_CUDA_KNN_SECOND_MIN", 2.f, 1.f, 32.f);
+    gp.second_max = (int)env_float("CWIPC_CUDA_KNN_SECOND_MAX", 150.f, 1.f, 1.0e6f);
     int maxdim = 1;
     for (int a = 0; a < 3; a++) {
         gp.gmin[a] = gmin[a];
@@ -923,16 +1172,33 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     const int kk = k + 1;
     const size_t smem = sizeof(KnnWarpSmem) * KT_WARPS;
     static std::once_flag once[64];
-    std::call_once(once[dev & 63], [&] { CWCU_CHECK(cudaFuncSetAttribute(knn_tile_kernel<KCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+    std::call_once(once[dev & 63], [&] {
+        CWCU_CHECK(cudaFuncSetAttribute(knn_tile_kernel<KCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CWCU_CHECK(cudaFuncSetAttribute(knn_second_kernel<KCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    });
     const size_t nitems = div_up(n, (size_t)32);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nitems, (size_t)KT_WARPS), (size_t)sm_count(dev) * KT_BLOCKS_PER_SM));
     launch("knn_tile_kernel", s, 28 * (size_t)n, [&] {
         knn_tile_kernel<KCAP><<<grid, KT_THREADS, smem, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, (uint32_t)nquery, far_list, far_count);
     });
     if (gp.top_level == 0) return; // one cell spans the cloud: the main pass is exact for every query
+    uint32_t second_from = 0xffffffffu; // number of queued queries from which the second scan runs (decided on the device)
+    // The second scan pays when the queue is long enough to fill the machine with 32-query warps and the open queries are each
+    // other's neighbours (raw, noisy clouds); on a small cloud (a downsampled frame: a few thousand isolated points in the
+    // queue) its per-group latency is not bought back.  Measured: 47 K-point frames -2..-5 % throughput, 1 M raw points -23 % time.
+    static const float second_from_n = env_float("CWIPC_CUDA_KNN_SECOND_FROM_N", 262144.f, 0.f, 4.0e9f);
+    if (gp.rc_far > gp.rc && (double)std::min(nquery, n) >= (double)second_from_n) {
+        static const float share = env_float("CWIPC_CUDA_KNN_SECOND_SHARE", 0.f, 0.f, 1.f);
+        second_from = (uint32_t)std::max(1.0, std::ceil((double)share * (double)std::min(nquery, n)));
+        // open queries with a bound within rc_far pitches: scanned once more, group by group; the rest goes to the second list
+        launch("knn_second_kernel", s, (size_t)0, [&] {
+            knn_second_kernel<KCAP><<<(unsigned)sm_count(dev) * KT_BLOCKS_PER_SM, KT_THREADS, smem, s>>>(spts, sorted, gp, kk, k, table, d_dist, d_kth, far_list, far_count, second_from,
+                                                                                                         far_list + (n + 64), far_count + 1);
+        });
+    }
     constexpr int KPL = KCAP > 32 ? 2 : 1;
     launch("knn_far_kernel", s, (size_t)0, [&] {
-        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 8, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, far_leaf_points());
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 8, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, second_from, far_leaf_points());
     });
 }
 
@@ -1000,7 +1266,7 @@ void knn_mean_distances_banded(const cwipc_point *in, size_t n, int k, float hin
     KnnIndex ix;
     build_index(ix, in, n, k, hint_spacing, bounds, dev, s, lut, bands);
     // a query is queued at most once
-    Scratch far_list((n + 64) * sizeof(FarEntry), s);
+    Scratch far_list(2 * (n + 64) * sizeof(FarEntry), s); // the main pass's queue, and what the second scan passes on
     const int kk = k + 1;
     auto go = [&](auto kcap) {
         run_knn<decltype(kcap)::value>(ix.spts.as<cwipc_point>(), ix.sorted, n, ix.gp, k, ix.table.as<uint2>(), d_dist, d_kth, std::min(nquery, n), far_list.as<FarEntry>(),

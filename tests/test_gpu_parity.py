@@ -11,12 +11,14 @@ import os
 
 import numpy as np
 import pytest
+import sys
 
 from cwipc_util_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 
 DT = synthetic.cwipc_point_numpy_dtype
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_small.npz")
 
 
@@ -692,3 +694,35 @@ def test_synthetic_source_generates_on_the_device(cw, npoints, angle):
         diff = np.abs(got[c].astype(int) - want[c].astype(int))
         assert diff.max(initial=0) <= 1 and np.count_nonzero(diff) <= 1
     gen.free()
+
+@pytest.mark.parametrize("env", [
+    {"CWIPC_CUDA_KNN_SECOND_FROM_N": "0"},                                                                   # the second scan on small clouds too
+    {"CWIPC_CUDA_KNN_SECOND_FROM_N": "0", "CWIPC_CUDA_KNN_RC_FAR": "3.5", "CWIPC_CUDA_KNN_SECOND_MAX": "100000", "CWIPC_CUDA_KNN_SECOND_MIN": "1"},  # every open query, boxes larger than the range list
+    {"CWIPC_CUDA_KNN_RC_FAR": "0"},                                                                          # never
+    {"CWIPC_CUDA_KNN_SECOND_FROM_N": "0", "CWIPC_CUDA_KNN_PITCH": "0.6"},                                     # small pitch: most queries open
+])
+def test_knn_passes_split_the_work_not_the_result(cw, orc, env):
+    """Main pass, second scan (knn_second_kernel) and tree search (knn_far_kernel) are three ways to the same exact
+    k+1 smallest distances; the tunables only move queries between them.  A child process runs with the tunables forced
+    (they are read once per process) and must reproduce the oracle's distances bit for bit, whole cloud and per tile."""
+    import subprocess
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import cwipc_util_b200 as cw; from cwipc_util_b200 import synthetic\n"
+            "out = []\n"
+            "for n, seed in ((90000, 31), (200000, 32)):\n"
+            "    pts = synthetic.camera_cloud(n, seed=seed, noise=0.004)\n"
+            "    pc = cw.cwipc_from_numpy_array(pts, 1); pc._set_cellsize(synthetic.cellsize_of(n))\n"
+            "    out.append(cw.util.knn_mean_distances(pc, 30).astype(np.float32).tobytes())\n"
+            "    out.append(cw.cwipc_remove_outliers(pc, 12, 1.5, True).get_numpy_array().tobytes())\n"
+            "sys.stdout.buffer.write(b''.join(out))" % REPO)
+    raw = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, check=True, timeout=900).stdout
+    pos = 0
+    for n, seed in ((90000, 31), (200000, 32)):
+        pts = synthetic.camera_cloud(n, seed=seed, noise=0.004)
+        d = np.frombuffer(raw[pos:pos + 4 * len(pts)], np.float32)   # (the generator rounds n to a square)
+        pos += 4 * len(pts)
+        assert np.array_equal(d, orc.knn_mean_distances(pts, 30))
+        want = download(cw.cwipc_remove_outliers(upload(cw, pts, cellsize=synthetic.cellsize_of(n)), 12, 1.5, True))
+        got = np.frombuffer(raw[pos:pos + want.nbytes], DT)
+        pos += want.nbytes
+        assert np.array_equal(got, want)
+    assert pos == len(raw)
