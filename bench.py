@@ -341,7 +341,15 @@ def measure_config4(cw, lib, peak):
         _, kernels = profiled(lambda: cw.cwipc_remove_outliers(cw.cwipc_downsample(pc, 0.005), K, STDDEV, False))
         chain = {"what": "downsample(0.005) -> remove_outliers(30, 1.0, perTile=False)", "voxels": v, "kept": m, "ms": round(ms, 4), "Mpoints_per_s": round(n / ms / 1e3, 1),
                  "frac": round(16.0 * (n + 2 * v + m) / ms / 1e6 / peak, 4), "kernels": kernels}
-        out["clouds"][name] = {"points": n, "downsample": rows, "chain": chain}
+        # outlier removal of the raw cloud itself (the north star's "8M-point ... outlier removal"): 16 B read per point + survivors written
+        for _ in range(2):   # (the first calls at this size grow the library's memory pool)
+            cw.cwipc_remove_outliers(pc, K, STDDEV, False).free()
+        ms, o = timed(lambda: cw.cwipc_remove_outliers(pc, K, STDDEV, False), reps=3)
+        m = o.count()
+        _, kernels = profiled(lambda: cw.cwipc_remove_outliers(pc, K, STDDEV, False))
+        raw = {"what": "remove_outliers(30, 1.0, perTile=False) of the raw cloud", "kept": m, "ms": round(ms, 4), "Mpoints_per_s": round(n / ms / 1e3, 1),
+               "frac": round(16.0 * (n + m) / ms / 1e6 / peak, 4), "kernels": kernels}
+        out["clouds"][name] = {"points": n, "downsample": rows, "chain": chain, "remove_outliers_raw": raw}
         pc.free()
     return out
 
@@ -374,9 +382,9 @@ def measure_slab(cw, dist, torch, rank, world):
     pc = cw.cwipc_from_numpy_array(part, 3)
     pc._set_cellsize(synthetic.cellsize_of(n_req))
 
-    def timed(fn, reps=3):
+    def timed(fn, reps=3, warm=1):
         times, res = [], None
-        for i in range(reps + 1):
+        for i in range(reps + warm):
             lib.cwipc_cuda_flush_l2()
             cw.cuda_synchronize()
             dist_barrier(dist, torch)
@@ -387,7 +395,7 @@ def measure_slab(cw, dist, torch, rank, world):
             cw.cuda_synchronize()
             ms = dist_reduce(dist, torch, lib.cwipc_cuda_timer_elapsed_ms(tm), "MAX")
             lib.cwipc_cuda_timer_destroy(tm)
-            if i >= 1:
+            if i >= warm:
                 times.append(ms)
         return float(np.median(times)), res
 
@@ -427,7 +435,8 @@ def measure_slab(cw, dist, torch, rank, world):
     m_in = int(dist_reduce(dist, torch, ds005.count(), "SUM"))
     out["rows"].append({"op": "remove_outliers of the downsample(0.005) result", "points": m_in, "kept": int(dist_reduce(dist, torch, o.count(), "SUM")), "ms": round(ms, 4),
                         "Mpoints_per_s": round(m_in / ms / 1e3, 1)})
-    ms, o = timed(lambda: comm.remove_outliers(pc, K, STDDEV, False), reps=2)
+    # (three warm-ups: the first calls at this size grow the library's memory pool by several hundred MB)
+    ms, o = timed(lambda: comm.remove_outliers(pc, K, STDDEV, False), reps=3, warm=3)
     out["rows"].append({"op": "remove_outliers of the raw cloud", "points": n_all, "kept": int(dist_reduce(dist, torch, o.count(), "SUM")), "ms": round(ms, 4),
                         "Mpoints_per_s": round(n_all / ms / 1e3, 1)})
     comm.free()

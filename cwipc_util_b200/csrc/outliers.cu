@@ -1124,7 +1124,12 @@ GridPlan choose_grid(const float gmin[3], const float gmax[3], size_t n, int k, 
     if (max_axis_bits < 2) throw CudaError{cudaErrorInvalidValue, "remove_outliers: too many points and tiles for one search index"};
     if (!(h > 0.0) || !std::isfinite(h)) h = 1.0;
     // the bands lie side by side along x, each padded to a power of two of cells (<= 2x on the longest axis)
-    const double cell_cap = (double)std::min<size_t>(std::max<size_t>(4 * n, (size_t)1 << 16), (size_t)1 << 25) / (bands > 1 ? 2.0 * (double)bands : 1.0);
+    // dense tables: 9.1 bytes per cell over all levels.  16 cells per point (146 MB at 1 M points), at most 2^27 cells
+    // (1.2 GB, reached from 8 M points on).  Round 1 allowed 4 per point / 2^25: an 8 M-point cloud and the per-tile bands of a
+    // 1 M-point cloud then got a pitch 1.6-2x the wanted one, i.e. 2.5-4x the candidates per query (8 M raw: 9.3 -> 6.5 ms).
+    static const float cells_per_point = env_float("CWIPC_CUDA_KNN_CELLS_PER_POINT", 16.f, 0.25f, 1024.f);
+    static const float max_cells_log2 = env_float("CWIPC_CUDA_KNN_MAX_CELLS_LOG2", 27.f, 16.f, 30.f);
+    const double cell_cap = std::min(std::max((double)cells_per_point * (double)n, 65536.0), std::ldexp(1.0, (int)max_cells_log2)) / (bands > 1 ? 2.0 * (double)bands : 1.0);
     while (true) {
         const double cells = (std::floor(ext[0] / h) + 2) * (std::floor(ext[1] / h) + 2) * (std::floor(ext[2] / h) + 2);
         if (longest / h < (double)((1 << max_axis_bits) - 1) && cells <= cell_cap) break;

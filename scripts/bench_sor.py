@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--raw", type=int, default=1000000)
+    ap.add_argument("--clean", action="store_true", help="the raw cloud is the clean synthetic cloud (as cwipc_synthetic generates it) instead of the jittered one")
     args = ap.parse_args()
     import bench
     import cwipc_util_b200 as cw
@@ -29,7 +30,8 @@ def main():
     pc = cw.cwipc_from_numpy_array(frame, 0)
     pc._set_cellsize(synthetic.cellsize_of(len(frame)))
     ds = cw.cwipc_downsample(pc, 0.01)
-    raw = cw.cwipc_from_numpy_array(synthetic.camera_cloud(args.raw, seed=0), 0)
+    raw_pts = synthetic.simulate_cameras(synthetic.synthetic_cloud(args.raw), 4) if args.clean else synthetic.camera_cloud(args.raw, seed=0)
+    raw = cw.cwipc_from_numpy_array(raw_pts, 0)
     raw._set_cellsize(synthetic.cellsize_of(args.raw))
 
     def timed(fn, reps):
