@@ -9,6 +9,8 @@ from cwipc_util_b200 import synthetic, util
 lib = util.cwipc_util_dll_load()
 n_req = 2828 * 2828
 pts = synthetic.simulate_cameras(synthetic.synthetic_cloud(n_req), 4)
+if len(sys.argv) > 1 and sys.argv[1] == "jittered":
+    pts = synthetic.add_outliers(synthetic.add_noise(pts, 0.002, 1), 0.005, 1)
 pc = cw.cwipc_from_numpy_array(pts, 3); pc._set_cellsize(synthetic.cellsize_of(n_req))
 comm = util.cuda_comm(None, 1, 0)
 
@@ -27,4 +29,5 @@ def run(fn, name):
     print(name, {k: round(v["total_ms"] * 1e3, 1) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["total_ms"])[:8]}, flush=True)
 
 run(lambda: cw.cwipc_remove_outliers(pc, 30, 1.0, False), "plain")
-run(lambda: comm.remove_outliers(pc, 30, 1.0, False), "slab1")
+if len(sys.argv) <= 2:
+    run(lambda: comm.remove_outliers(pc, 30, 1.0, False), "slab1")
