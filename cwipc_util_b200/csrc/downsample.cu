@@ -1433,11 +1433,14 @@ void launch_stream(const StreamArgs &args, const KeyTables &tab, int dev, cudaSt
     static std::once_flag once[64];
     std::call_once(once[dev & 63], [&] {
         CWCU_CHECK(cudaFuncSetAttribute(voxel_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_SMEM_BYTES));
-        CWCU_CHECK(cudaFuncSetAttribute(voxel_stream_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared)); // two blocks per SM
     });
+    // two blocks of 106 KB per SM need the largest carve-out ($CWIPC_CUDA_DS_CARVEOUT, $CWIPC_CUDA_DS_BLOCKS_PER_SM: tuning only)
+    static const int carveout = [] { const char *e = getenv("CWIPC_CUDA_DS_CARVEOUT"); return e && *e ? atoi(e) : (int)cudaSharedmemCarveoutMaxShared; }();
+    static const size_t blocks_per_sm = [] { const char *e = getenv("CWIPC_CUDA_DS_BLOCKS_PER_SM"); return (size_t)std::max(1, std::min(2, e && *e ? atoi(e) : 2)); }();
+    tune_kernel(voxel_stream_kernel<MODE>, carveout, true);
     // persistent warps: two blocks of eight warps per SM, every warp takes tiles gw, gw + nw, ...
     static const size_t tiles_per_warp = [] { const char *e = getenv("CWIPC_CUDA_DS_TILES_PER_WARP"); return (size_t)std::max(1, e && *e ? atoi(e) : 1); }(); // tuning only
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up((size_t)args.ntiles, (size_t)VS_WARPS * tiles_per_warp), (size_t)sm_count(dev) * 2));
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up((size_t)args.ntiles, (size_t)VS_WARPS * tiles_per_warp), (size_t)sm_count(dev) * blocks_per_sm));
     launch("voxel_stream_kernel", s, 16 * (size_t)args.n, [&] { voxel_stream_kernel<MODE><<<grid, VS_THREADS, VS_SMEM_BYTES, s>>>(args, tab); });
 }
 
@@ -1624,6 +1627,8 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
                 return result;
             }
             Scratch words(v * sizeof(uint64_t), s), other(v * sizeof(uint64_t), s);
+            tune_kernel(voxel_words_kernel, CHAIN_CARVEOUT);
+            tune_kernel(voxel_emit_kernel, CHAIN_CARVEOUT);
             launch("voxel_words_kernel", s, 16 * v, [&] {
                 voxel_words_kernel<<<(unsigned)std::max<size_t>(1, div_up(v, 256)), 256, 0, s>>>(list_keys.as<uint64_t>(), (uint32_t)v, cbits, fused ? 1 : 0, ob.shift[0], ob.shift[1], ob.shift[2],
                                                                                                  depth, words.as<uint64_t>(), header);

@@ -733,32 +733,114 @@ __device__ __forceinline__ float list_absorb(float (&v)[KPL], float d2, bool pas
     return __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
 }
 
+// Where a search starts: the root (level < 0), or the (at most) 2x2x2 nodes of `level` from (x, y, z) on, which are known to
+// hold every point within sqrt(limit) of the query.
+struct FarStart {
+    int level;
+    uint32_t x, y, z;
+};
+
 // The kk nearest squared distances from q to the cloud, ascending along (lane, register): element e
 // lives in lane e % 32, register e / 32.  Called by all 32 lanes of a warp with the same arguments.
 // Every iteration takes the (up to) four nearest open nodes off the stack: the small ones are scanned, the
 // others are expanded together, eight lanes per node, one child per lane.
 template <int KPL>
 __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Point16 *__restrict__ spts16, uint32_t n, const GridParams &gp, int kk,
-                                        const uint2 *__restrict__ table, uint32_t leaf_points, FarNode *stack, float (&v)[KPL], uint32_t band = 0u) {
+                                        const uint2 *__restrict__ table, uint32_t leaf_points, FarNode *stack, float (&v)[KPL], uint32_t band = 0u,
+                                        const FarStart start = FarStart{-1, 0u, 0u, 0u}) {
     const unsigned lane = lane_id();
     const float slack = 0.01f * gp.h;
 #pragma unroll
     for (int j = 0; j < KPL; j++) v[j] = INFINITY;
     float tau = INFINITY; // current kk-th smallest
+    int sp = 0;
 
-    if (lane == 0) {
-        FarNode root;
-        root.pb = 0; root.pe = n; root.xy = 0; root.zl = (uint32_t)gp.top_level << 16; root.mind2 = 0.f;
-        if (gp.bands > 1) { // per-tile mode: the search never leaves the query's band, the level-band_bits node (band, 0, 0)
-            const uint2 r = table[table_index(gp, gp.band_bits, band, 0u, 0u)];
-            root.pb = r.x; root.pe = r.y; root.xy = band; root.zl = (uint32_t)gp.band_bits << 16;
+    // Children of open nodes (one per lane) -> stack, nearest on top.  A lane that `want`s its node (cl, chx, chy, chz) reads
+    // the node's point range, drops it when empty or farther than `thr`, and the survivors are ranked by (distance, lane).
+    auto push_nodes = [&](bool want, int cl, uint32_t chx, uint32_t chy, uint32_t chz, float thr) {
+        uint2 r = make_uint2(0u, 0u);
+        float mind2 = INFINITY;
+        bool admit = false;
+        if (want && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl) &&
+            (gp.bands <= 1 || (chx >> (gp.band_bits - cl)) == band)) { // (children of a band's node stay inside the band; start nodes might not)
+            r = table[table_index(gp, cl, chx, chy, chz)];
+            if (r.y > r.x) {
+                const float pitch = ldexpf(gp.h, cl);
+                const uint32_t lx = chx - (band << (gp.band_bits - cl)); // x within the band (band == 0 outside the per-tile mode)
+                const float lo[3] = {gp.gmin[0] + (float)lx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
+                const float qq[3] = {q.x, q.y, q.z};
+                mind2 = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
+                    mind2 += d * d;
+                }
+                admit = mind2 * 0.9999f <= thr;
+            }
         }
-        stack[0] = root;
+        const unsigned adm = __ballot_sync(FULL_MASK, admit);
+        if (adm == 0u) return;
+        const int nadm = __popc(adm);
+        FarNode ch;
+        ch.pb = r.x; ch.pe = r.y; ch.xy = chx | (chy << 16); ch.zl = chz | ((uint32_t)cl << 16); ch.mind2 = mind2;
+        if (nadm <= 12) {
+            // few survivors (the usual case once a bound is known): every lane counts the admitted nodes in front of its own
+            const uint32_t mine = __float_as_uint(mind2); // non-negative floats: the bit patterns order like the values
+            int rank = 0;
+            for (unsigned m = adm; m; m &= m - 1u) {
+                const int src = __ffs(m) - 1;
+                const uint32_t other = __shfl_sync(FULL_MASK, mine, src);
+                rank += (other < mine || (other == mine && src < (int)lane)) ? 1 : 0;
+            }
+            if (admit) stack[sp + nadm - 1 - rank] = ch; // farthest deepest, nearest on top
+        } else {
+            // many: a 32-lane bitonic sort of (distance, lane) keys
+            unsigned long long key = admit ? (((unsigned long long)__float_as_uint(mind2) << 32) | lane) : ~0ull;
+#pragma unroll
+            for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(FULL_MASK, key, j2);
+                    const bool up = (lane & (unsigned)k2) == 0u;
+                    const bool lower = (lane & (unsigned)j2) == 0u;
+                    key = (lower == up) ? (key < other ? key : other) : (key < other ? other : key);
+                }
+            }
+            // lane i now holds the i-th nearest admitted node's (distance, source lane); fetch that node and store it
+            const int src = (int)(key & 31u);
+            FarNode sorted_ch;
+            sorted_ch.pb = __shfl_sync(FULL_MASK, ch.pb, src);
+            sorted_ch.pe = __shfl_sync(FULL_MASK, ch.pe, src);
+            sorted_ch.xy = __shfl_sync(FULL_MASK, ch.xy, src);
+            sorted_ch.zl = __shfl_sync(FULL_MASK, ch.zl, src);
+            sorted_ch.mind2 = __shfl_sync(FULL_MASK, ch.mind2, src);
+            if ((int)lane < nadm) stack[sp + nadm - 1 - (int)lane] = sorted_ch;
+        }
+        sp += nadm;
+    };
+
+    bool from_start = start.level >= 0;
+    if (!from_start) {
+        if (lane == 0) {
+            FarNode root;
+            root.pb = 0; root.pe = n; root.xy = 0; root.zl = (uint32_t)gp.top_level << 16; root.mind2 = 0.f;
+            if (gp.bands > 1) { // per-tile mode: the search never leaves the query's band, the level-band_bits node (band, 0, 0)
+                const uint2 r = table[table_index(gp, gp.band_bits, band, 0u, 0u)];
+                root.pb = r.x; root.pe = r.y; root.xy = band; root.zl = (uint32_t)gp.band_bits << 16;
+            }
+            stack[0] = root;
+        }
+        sp = 1;
     }
-    int sp = 1;
     __syncwarp();
     const int group = (int)(lane >> 3);
-    while (sp > 0) {
+    while (from_start || sp > 0) {
+        if (from_start) { // the first step lists the start nodes instead of the children of open nodes
+            from_start = false;
+            push_nodes(lane < 8u, start.level, start.x + ((lane >> 2) & 1u), start.y + ((lane >> 1) & 1u), start.z + (lane & 1u), limit);
+            __syncwarp();
+            continue;
+        }
         const int take = min(sp, 4);
         // lane group g looks at the g-th node from the top (g = 0 is the nearest)
         const FarNode node = stack[sp - 1 - min(group, take - 1)];
@@ -788,61 +870,76 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
         const bool expand = have && !(node_level == 0 || node.pe - node.pb <= leaf_points) && !(node.mind2 * 0.9999f > thr);
         const int cl = node_level - 1;
         const uint32_t chx = 2u * node_x + ((lane >> 2) & 1u), chy = 2u * node_y + ((lane >> 1) & 1u), chz = 2u * node_z + (lane & 1u);
-        uint2 r = make_uint2(0u, 0u);
-        float mind2 = INFINITY;
-        bool admit = false;
-        if (expand && chx < (uint32_t)level_dim(gp.gdim[0], cl) && chy < (uint32_t)level_dim(gp.gdim[1], cl) && chz < (uint32_t)level_dim(gp.gdim[2], cl)) {
-            r = table[table_index(gp, cl, chx, chy, chz)];
-            if (r.y > r.x) {
-                const float pitch = ldexpf(gp.h, cl);
-                const uint32_t lx = chx - (band << (gp.band_bits - cl)); // x within the band (band == 0 outside the per-tile mode)
-                const float lo[3] = {gp.gmin[0] + (float)lx * pitch, gp.gmin[1] + (float)chy * pitch, gp.gmin[2] + (float)chz * pitch};
-                const float qq[3] = {q.x, q.y, q.z};
-                mind2 = 0.f;
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const float d = fmaxf(fmaxf(lo[a] - qq[a], qq[a] - (lo[a] + pitch)) - slack, 0.f);
-                    mind2 += d * d;
-                }
-                admit = mind2 * 0.9999f <= thr;
-            }
-        }
-        const unsigned adm = __ballot_sync(FULL_MASK, admit);
-        if (adm) {
-            const int nadm = __popc(adm);
-            // position among the admitted children, nearest first: a 32-lane bitonic sort of (distance, lane) keys
-            // (distances are non-negative floats: their bit patterns order like the values)
-            unsigned long long key = admit ? (((unsigned long long)__float_as_uint(mind2) << 32) | lane) : ~0ull;
-#pragma unroll
-            for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-                for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(FULL_MASK, key, j2);
-                    const bool up = (lane & (unsigned)k2) == 0u;
-                    const bool lower = (lane & (unsigned)j2) == 0u;
-                    key = (lower == up) ? (key < other ? key : other) : (key < other ? other : key);
-                }
-            }
-            // lane i now holds the i-th nearest admitted child's (distance, source lane); fetch that child and store it
-            const int src = (int)(key & 31u);
-            FarNode ch;
-            ch.pb = __shfl_sync(FULL_MASK, r.x, src);
-            ch.pe = __shfl_sync(FULL_MASK, r.y, src);
-            ch.xy = __shfl_sync(FULL_MASK, chx | (chy << 16), src);
-            ch.zl = __shfl_sync(FULL_MASK, chz | ((uint32_t)cl << 16), src);
-            ch.mind2 = __shfl_sync(FULL_MASK, mind2, src);
-            if ((int)lane < nadm) stack[sp + nadm - 1 - (int)lane] = ch; // farthest deepest, nearest on top
-            sp += nadm;
-        }
+        push_nodes(expand, cl, chx, chy, chz, thr);
         __syncwarp();
     }
 }
 
+// Start of the search for a query that is a point of the cloud itself (Morton code of its cell: `code`).  The smallest node
+// around its cell that holds kk points or more bounds the kk-th distance by the distance to that node's farthest corner
+// (one table entry per level, one level per lane); `limit` is lowered to that bound.  Every point within the bound then
+// lies in at most 2x2x2 nodes of some level L, and the search starts there instead of at the root: an isolated point
+// (what the main pass leaves open on a downsampled frame) no longer descends through the whole pyramid with no bound at all.
+__device__ __forceinline__ FarStart far_start(const Point16 q, uint64_t code, const GridParams &gp, int kk, const uint2 *__restrict__ table, uint32_t band, float &limit) {
+    const unsigned lane = lane_id();
+    const uint32_t cx = compact3(code >> 2), cy = compact3(code >> 1), cz = compact3(code);
+    const int root_level = gp.bands > 1 ? gp.band_bits : gp.top_level;
+    const float slack = 0.01f * gp.h; // a point may sit this far outside the nominal box of its cell (rounding of cell_u)
+    const float qq[3] = {q.x, q.y, q.z};
+    bool enough = false;
+    float far2 = INFINITY;
+    if ((int)lane <= root_level) {
+        const int l = (int)lane;
+        const uint32_t ax = cx >> l, ay = cy >> l, az = cz >> l;
+        const uint2 r = table[table_index(gp, l, ax, ay, az)];
+        if (r.y - r.x >= (uint32_t)kk) {
+            enough = true;
+            const float pitch = ldexpf(gp.h, l);
+            const uint32_t lx = ax - (band << (gp.band_bits - l));
+            const float lo[3] = {gp.gmin[0] + (float)lx * pitch, gp.gmin[1] + (float)ay * pitch, gp.gmin[2] + (float)az * pitch};
+            far2 = 0.f;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float d = fmaxf(qq[a] - lo[a], (lo[a] + pitch) - qq[a]) + slack;
+                far2 += d * d;
+            }
+        }
+    }
+    FarStart st;
+    st.level = -1;
+    st.x = st.y = st.z = 0u;
+    const unsigned m = __ballot_sync(FULL_MASK, enough);
+    if (m != 0u) limit = fminf(limit, __shfl_sync(FULL_MASK, far2, __ffs(m) - 1) * 1.0001f);
+    if (!(limit < INFINITY)) return st; // fewer than kk points in the band / the cloud and no bound from the main pass: from the root
+    // cells that can hold a point within the bound (cell units, 0.02 covers the rounding of cell_u on both sides)
+    const float rcells = sqrtf(limit) * gp.inv_h * 1.000001f + 0.02f;
+    const float u[3] = {cell_u(q.x, gp.gmin[0], gp.inv_h), cell_u(q.y, gp.gmin[1], gp.inv_h), cell_u(q.z, gp.gmin[2], gp.inv_h)};
+    const int dim[3] = {gp.xdim, gp.gdim[1], gp.gdim[2]};
+    uint32_t lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        lo[a] = (uint32_t)min(max((int)floorf(u[a] - rcells), 0), dim[a] - 1);
+        hi[a] = (uint32_t)min(max((int)floorf(u[a] + rcells), 0), dim[a] - 1);
+    }
+    lo[0] += band << gp.band_bits;
+    hi[0] += band << gp.band_bits;
+    for (int l = 0; l < root_level; l++) {
+        if ((hi[0] >> l) - (lo[0] >> l) <= 1u && (hi[1] >> l) - (lo[1] >> l) <= 1u && (hi[2] >> l) - (lo[2] >> l) <= 1u) {
+            st.level = l;
+            st.x = lo[0] >> l;
+            st.y = lo[1] >> l;
+            st.z = lo[2] >> l;
+            break;
+        }
+    }
+    return st;
+}
+
 template <int KPL>
-__global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, GridParams gp, int kk, int k,
+__global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *__restrict__ spts, const uint64_t *__restrict__ sorted, uint32_t n, const __grid_constant__ GridParams gp, int kk, int k,
                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out,
                                                               const FarEntry *__restrict__ far_list, const uint32_t *__restrict__ far_count, uint32_t second_from,
-                                                              uint32_t leaf_points) {
+                                                              uint32_t leaf_points, bool far_start_enabled) {
     __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     // when the second scan ran (the main pass queued at least second_from queries) the list it passed on is the one to
@@ -858,8 +955,15 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
     for (uint32_t ei = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ei < nentries; ei += warps_total) {
         const FarEntry ent = far_list[ei];
         float v[KPL];
-        const uint32_t band = gp.bands > 1 ? (compact3((sorted[ent.q] >> gp.idxbits) >> 2) >> gp.band_bits) : 0u;
-        dfs_knn<KPL>(spts16[ent.q], ent.bound, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v, band);
+        const uint64_t code = sorted[ent.q] >> gp.idxbits;
+        const uint32_t band = gp.bands > 1 ? (compact3(code >> 2) >> gp.band_bits) : 0u;
+        const Point16 q = spts16[ent.q];
+        float limit = ent.bound;
+        FarStart start;
+        start.level = -1;
+        start.x = start.y = start.z = 0u;
+        if (far_start_enabled) start = far_start(q, code, gp, kk, table, band, limit);
+        dfs_knn<KPL>(q, limit, spts16, n, gp, kk, table, leaf_points, s_stack[warp], v, band, start);
         // sum of sqrt over elements 1..k in ascending order (double), as the reference does
         double sq[KPL];
 #pragma unroll
@@ -1183,6 +1287,7 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     });
     const size_t nitems = div_up(n, (size_t)32);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nitems, (size_t)KT_WARPS), (size_t)sm_count(dev) * KT_BLOCKS_PER_SM));
+    tune_kernel(knn_tile_kernel<KCAP>, CHAIN_CARVEOUT);
     launch("knn_tile_kernel", s, 28 * (size_t)n, [&] {
         knn_tile_kernel<KCAP><<<grid, KT_THREADS, smem, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, (uint32_t)nquery, far_list, far_count);
     });
@@ -1196,14 +1301,19 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
         static const float share = env_float("CWIPC_CUDA_KNN_SECOND_SHARE", 0.f, 0.f, 1.f);
         second_from = (uint32_t)std::max(1.0, std::ceil((double)share * (double)std::min(nquery, n)));
         // open queries with a bound within rc_far pitches: scanned once more, group by group; the rest goes to the second list
+        tune_kernel(knn_second_kernel<KCAP>, CHAIN_CARVEOUT);
         launch("knn_second_kernel", s, (size_t)0, [&] {
             knn_second_kernel<KCAP><<<(unsigned)sm_count(dev) * KT_BLOCKS_PER_SM, KT_THREADS, smem, s>>>(spts, sorted, gp, kk, k, table, d_dist, d_kth, far_list, far_count, second_from,
                                                                                                          far_list + (n + 64), far_count + 1);
         });
     }
     constexpr int KPL = KCAP > 32 ? 2 : 1;
+    tune_kernel(knn_far_kernel<KPL>, CHAIN_CARVEOUT);
     launch("knn_far_kernel", s, (size_t)0, [&] {
-        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 8, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, second_from, far_leaf_points());
+        // CWIPC_CUDA_KNN_FAR_START=0 (tests / A-B only): every search starts at the root with no bound, as in round 1
+        static const bool far_start_on = env_float("CWIPC_CUDA_KNN_FAR_START", 1.f, 0.f, 1.f) != 0.f;
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 8, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, kk, k, table, d_dist, d_kth, far_list, far_count, second_from, far_leaf_points(),
+                                                                               far_start_on);
     });
 }
 
@@ -1243,6 +1353,8 @@ void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hin
     ix.spts = Scratch(n * sizeof(cwipc_point), s);
     ix.table = Scratch((plan.table_entries + 2) * sizeof(uint2), s);
     ix.far_count = reinterpret_cast<uint32_t *>(ix.table.as<uint2>() + plan.table_entries);
+    tune_kernel(knn_keygen_kernel, CHAIN_CARVEOUT);
+    tune_kernel(knn_layout_kernel, CHAIN_CARVEOUT);
     launch("knn_keygen_kernel", s, 24 * (size_t)n, [&] {
         knn_keygen_kernel<<<stream_grid(std::max(n, plan.table_entries / 4), dev), 256, 0, s>>>(in, (uint32_t)n, gp, band_lut, ix.keys_a.as<uint64_t>(), ix.table.as<uint2>(),
                                                                                                  (uint32_t)(plan.table_entries + 2));
@@ -1419,6 +1531,7 @@ size_t remove_outliers_points(const cwipc_point *in, size_t n, cwipc_point *out,
     Scratch partial((2 * ST_BLOCKS + 1) * sizeof(double), s);
     uint32_t *counter = static_cast<uint32_t *>(thread_zeroed(dev, ZW_HEADER_BYTES, s)) + 6; // word 6 of the zeroed workspace header
     double *d_thr = partial.as<double>() + 2 * ST_BLOCKS;
+    tune_kernel(stats_threshold_kernel, CHAIN_CARVEOUT);
     launch("stats_kernel", s, 4 * (size_t)n, [&] {
         stats_threshold_kernel<<<ST_BLOCKS, ST_THREADS, 0, s>>>(dist.as<float>(), (uint32_t)n, partial.as<double>(), counter, (double)stddev_mul, d_thr);
     });

@@ -56,13 +56,12 @@ DevicePointcloud *DevicePointcloud::from_host(const cwipc_point *points, size_t 
     DeviceGuard g(dev);
     auto store = std::make_shared<Storage>(dev, npoint, s);
     store->count = npoint;
-    if (npoint) {
-        CWCU_CHECK(cudaMemcpyAsync(store->d_pts, points, npoint * sizeof(cwipc_point), cudaMemcpyHostToDevice, s));
-    }
+    // Pageable source memory has been read completely when copy_from_host returns (it travels through the calling
+    // thread's page-locked ring); page-locked memory is read by the DMA engine later, so wait unless the caller opted out.
+    bool pinned = false;
+    if (npoint) pinned = copy_from_host(store->d_pts, points, npoint * sizeof(cwipc_point), s);
     store->mark_ready();
-    // Pageable source memory has already been staged by the driver when cudaMemcpyAsync returns;
-    // page-locked memory is read by the DMA engine later, so wait unless the caller opted out.
-    if (sync && npoint && is_pinned_host(points)) stream_sync(s);
+    if (sync && npoint && pinned) stream_sync(s);
     return new DevicePointcloud(store, timestamp, 0.f);
 }
 
@@ -132,9 +131,8 @@ int DevicePointcloud::copy_uncompressed(struct cwipc_point *pointbuf, size_t siz
         DeviceGuard g(st->dev);
         cudaStream_t s = thread_stream(st->dev);
         st->acquire_for_read(s);
-        CWCU_CHECK(cudaMemcpyAsync(pointbuf, st->d_pts, need, cudaMemcpyDeviceToHost, s));
+        copy_to_host(pointbuf, st->d_pts, need, s); // returns when pointbuf is complete
         st->release_after_read(s);
-        stream_sync(s);
         return (int)st->count;
     });
 }
@@ -185,7 +183,7 @@ StoragePtr storage_of(cwipc_pointcloud *pc, const char *who) {
         DeviceGuard g(dev);
         auto store = std::make_shared<Storage>(dev, n, s);
         store->count = n;
-        if (n) CWCU_CHECK(cudaMemcpyAsync(store->d_pts, host.data(), bytes, cudaMemcpyHostToDevice, s));
+        if (n) (void)copy_from_host(store->d_pts, host.data(), bytes, s);
         store->mark_ready();
         stream_sync(s);
         return store;

@@ -1,6 +1,7 @@
 // runtime.cu -- streams, memory pool, storage lifetime, launch accounting.  See runtime.hpp.
 #include "runtime.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -97,6 +98,16 @@ struct ThreadState {
         bool dirty = false;
     };
     std::vector<Zeroed> zeroed; // per device
+    // page-locked staging ring for copies from / to pageable caller memory (copy_from_host / copy_to_host)
+    static constexpr int STAGE_SLOTS = 4;
+    static constexpr size_t STAGE_CHUNK = (size_t)2 << 20;
+    struct Stage {
+        char *ring = nullptr;
+        cudaEvent_t done[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr}; // the last transfer that used the slot
+        int dev[STAGE_SLOTS] = {-1, -1, -1, -1};                              // device that event was created on
+        bool pending[STAGE_SLOTS] = {false, false, false, false};
+        unsigned next = 0;
+    } stage;
     ~ThreadState() {
         // give streams back so that thread churn does not leak them
         if (g_devs) {
@@ -365,6 +376,143 @@ void stream_sync(cudaStream_t s) {
         }
     }
     CWCU_CHECK(cudaEventSynchronize(ev)); // blocks (cudaEventBlockingSync): the thread sleeps until the GPU interrupt
+}
+
+// ------------------------------------------------------------------------------------------
+// staged copies from / to pageable host memory
+// ------------------------------------------------------------------------------------------
+namespace {
+bool staging_enabled() {
+    static const bool on = [] { const char *e = getenv("CWIPC_CUDA_STAGING"); return !(e && *e == '0'); }();
+    return on;
+}
+constexpr size_t STAGE_MIN_BYTES = (size_t)1 << 20; // below this the driver's own path is as good
+
+void host_wait_event(cudaEvent_t ev) {
+    timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    while (true) {
+        const cudaError_t q = cudaEventQuery(ev);
+        if (q == cudaSuccess) return;
+        if (q != cudaErrorNotReady) throw_cuda(q, "cudaEventQuery(stage)", __FILE__, __LINE__);
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if ((t1.tv_sec - t0.tv_sec) * 1000000000L + (t1.tv_nsec - t0.tv_nsec) >= 30000L) { // a chunk takes 40-200 us: nap between polls
+            const timespec nap = {0, 10000L};
+            nanosleep(&nap, nullptr);
+        }
+    }
+}
+
+struct StageRing {
+    ThreadState::Stage &st;
+    int dev;
+    explicit StageRing(int dev_) : st(t_state.stage), dev(dev_) {
+        if (!st.ring) {
+            void *p = nullptr;
+            CWCU_CHECK(cudaHostAlloc(&p, ThreadState::STAGE_SLOTS * ThreadState::STAGE_CHUNK, cudaHostAllocPortable));
+            st.ring = static_cast<char *>(p);
+        }
+    }
+    char *slot(int i) const { return st.ring + (size_t)i * ThreadState::STAGE_CHUNK; }
+    void wait(int i) { // until the last transfer that used slot i is done
+        if (st.pending[i]) {
+            host_wait_event(st.done[i]);
+            st.pending[i] = false;
+        }
+    }
+    void record(int i, cudaStream_t s) {
+        if (st.done[i] && st.dev[i] != dev) { // an event belongs to the device it was created on
+            (void)cudaEventDestroy(st.done[i]);
+            st.done[i] = nullptr;
+        }
+        if (!st.done[i]) {
+            CWCU_CHECK(cudaEventCreateWithFlags(&st.done[i], cudaEventDisableTiming));
+            st.dev[i] = dev;
+        }
+        CWCU_CHECK(cudaEventRecord(st.done[i], s));
+        st.pending[i] = true;
+    }
+};
+} // namespace
+
+bool copy_from_host(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return false;
+    const bool pinned = is_pinned_host(src);
+    if (pinned || bytes < STAGE_MIN_BYTES || !staging_enabled()) {
+        CWCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return pinned;
+    }
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    StageRing ring(dev);
+    for (size_t off = 0; off < bytes; off += ThreadState::STAGE_CHUNK) {
+        const size_t len = std::min(ThreadState::STAGE_CHUNK, bytes - off);
+        const int i = (int)ring.st.next;
+        ring.st.next = (ring.st.next + 1) % ThreadState::STAGE_SLOTS;
+        ring.wait(i);
+        memcpy(ring.slot(i), static_cast<const char *>(src) + off, len);
+        CWCU_CHECK(cudaMemcpyAsync(static_cast<char *>(dst) + off, ring.slot(i), len, cudaMemcpyHostToDevice, s));
+        ring.record(i, s);
+    }
+    return false;
+}
+
+void copy_to_host(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return;
+    if (bytes < STAGE_MIN_BYTES || !staging_enabled() || is_pinned_host(dst)) {
+        CWCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        stream_sync(s);
+        return;
+    }
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    StageRing ring(dev);
+    constexpr int SLOTS = ThreadState::STAGE_SLOTS;
+    const size_t chunk = ThreadState::STAGE_CHUNK, nchunks = (bytes + chunk - 1) / chunk;
+    // chunk c travels through slot (base + c) % SLOTS; up to SLOTS transfers are in flight while the oldest is copied out
+    const unsigned base = ring.st.next;
+    auto issue = [&](size_t c) {
+        const int i = (int)((base + c) % SLOTS);
+        ring.wait(i);
+        const size_t off = c * chunk, len = std::min(chunk, bytes - off);
+        CWCU_CHECK(cudaMemcpyAsync(ring.slot(i), static_cast<const char *>(src) + off, len, cudaMemcpyDeviceToHost, s));
+        ring.record(i, s);
+    };
+    for (size_t c = 0; c < std::min<size_t>(nchunks, SLOTS); c++) issue(c);
+    for (size_t c = 0; c < nchunks; c++) {
+        const int i = (int)((base + c) % SLOTS);
+        ring.wait(i);
+        const size_t off = c * chunk, len = std::min(chunk, bytes - off);
+        memcpy(static_cast<char *>(dst) + off, ring.slot(i), len);
+        if (c + SLOTS < nchunks) issue(c + SLOTS);
+    }
+    ring.st.next = (unsigned)((base + nchunks) % SLOTS);
+}
+
+void tune_kernel(const void *func, int dflt, bool fixed) {
+    static const int forced = [] {
+        const char *e = getenv("CWIPC_CUDA_CARVEOUT");
+        return (e && *e) ? atoi(e) : -2;
+    }();
+    const int want = (!fixed && forced >= -1) ? forced : dflt;
+    if (want < -1) return;
+    int dev = 0;
+    CWCU_CHECK(cudaGetDevice(&dev));
+    // applied once per (kernel, device); the per-thread list keeps the steady-state launch path free of locks
+    thread_local std::vector<std::pair<const void *, int>> seen;
+    for (const auto &e : seen)
+        if (e.first == func && e.second == dev) return;
+    seen.emplace_back(func, dev);
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> done;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done.find({func, dev});
+        if (it != done.end() && it->second == want) return;
+        done[{func, dev}] = want;
+    }
+    CWCU_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, want));
 }
 
 bool is_pinned_host(const void *p) {

@@ -61,6 +61,16 @@ void dfree(void *p, cudaStream_t s) noexcept;
 // Small page-locked scratch owned by the calling thread (count readbacks etc.), >= bytes, 16B aligned.
 void *thread_pinned(size_t bytes);
 bool is_pinned_host(const void *p);
+// Host <-> device copies of point buffers for callers that hand us ordinary (pageable) memory, as an unchanged
+// python/cwipc/util.py caller does.  The driver stages such copies itself, one caller at a time; here every caller
+// thread copies through its OWN page-locked ring (4 x 2 MB), chunk by chunk, so that the host-side memcpy of one chunk
+// overlaps the DMA of the one before it and the copies of several threads overlap each other.  Page-locked
+// memory and small buffers take the plain cudaMemcpyAsync.  $CWIPC_CUDA_STAGING=0 switches the ring off.
+//   copy_from_host: returns once `src` has been read completely (the transfer itself may still be in flight on `s`);
+//                   returns true when `src` was page-locked (the DMA engine reads it later: the caller decides whether to wait).
+//   copy_to_host:   returns once `dst` holds the bytes.
+bool copy_from_host(void *dst, const void *src, size_t bytes, cudaStream_t s);
+void copy_to_host(void *dst, const void *src, size_t bytes, cudaStream_t s);
 // Device workspace owned by the calling thread (one per device), at least `bytes` long, that is ALL
 // ZERO when handed out and that the caller must leave all zero again (the kernel that consumes an
 // entry clears it), so that steady-state calls need no memset.  Work on it must be queued on `s`,
@@ -166,6 +176,15 @@ inline void launch(const char *name, cudaStream_t s, size_t algorithmic_bytes, F
     f();
     check_launch(name);
 }
+// Shared-memory carve-out preference of a kernel (a percentage of the SM's shared memory, cudaSharedmemCarveoutMaxShared
+// = 100, or -1 = the driver's choice), applied once per kernel and device.  Kernels of several streams can only share an
+// SM when its L1 / shared-memory split suits them all, so the kernels of the frame chain state a common preference;
+// `dflt` < -1 leaves the kernel alone.  $CWIPC_CUDA_CARVEOUT overrides `dflt` for every kernel (tuning only).
+constexpr int CHAIN_CARVEOUT = -2; // default preference of the frame chain's kernels (-2: none stated)
+void tune_kernel(const void *func, int dflt, bool fixed = false); // fixed: $CWIPC_CUDA_CARVEOUT does not apply
+template <class K>
+inline void tune_kernel(K *kernel, int dflt, bool fixed = false) { tune_kernel(reinterpret_cast<const void *>(kernel), dflt, fixed); }
+
 // bytes that are only known after a readback (e.g. survivors written by a compaction)
 void profile_add_bytes(const char *name, size_t bytes);
 

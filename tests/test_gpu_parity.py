@@ -72,6 +72,42 @@ def test_from_points_roundtrip_and_empty(cw):
     assert np.array_equal(download(upload(cw, big)), big)
 
 
+def test_pageable_copies_through_the_staging_ring(cw):
+    """cwipc_from_points / copy_uncompressed with ordinary (pageable) caller memory travel through the calling thread's
+    page-locked ring in 2 MB chunks (csrc/runtime.cu: copy_from_host / copy_to_host): sizes around the 1 MB threshold and
+    the chunk edges, more chunks than ring slots, back-to-back calls reusing slots in flight, and four threads at once."""
+    import threading
+    sizes = [65535, 65536, 65537, 131071, 131072, 131073, 4 * 131072, 4 * 131072 + 1, 1000003, 2500000]
+    clouds = {n: random_cloud(n, seed=n % 97) for n in sizes}
+    pcs = [(n, upload(cw, clouds[n])) for n in sizes]          # uploads back to back: ring slots still in flight
+    for n, pc in pcs:
+        assert pc.count() == n
+        assert np.array_equal(download(pc), clouds[n]), n
+        pc.free()
+    errors = []
+
+    def worker(seed):
+        try:
+            cw.cuda_set_device(0)
+            for rep in range(3):
+                pts = random_cloud(700001 + 4099 * seed, seed=seed * 10 + rep)
+                pc = upload(cw, pts)
+                d = cw.cwipc_tilefilter(pc, 2)
+                assert np.array_equal(download(pc), pts)
+                assert np.array_equal(download(d), pts[pts["tile"] == 2])
+                d.free()
+                pc.free()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_from_points_size_mismatch_raises(cw, lib):
     cw.cwipc_log_configure(cw.CWIPC_LOG_LEVEL_NONE, lambda level, msg: None)
     try:
@@ -700,6 +736,8 @@ def test_synthetic_source_generates_on_the_device(cw, npoints, angle):
     {"CWIPC_CUDA_KNN_SECOND_FROM_N": "0", "CWIPC_CUDA_KNN_RC_FAR": "3.5", "CWIPC_CUDA_KNN_SECOND_MAX": "100000", "CWIPC_CUDA_KNN_SECOND_MIN": "1"},  # every open query, boxes larger than the range list
     {"CWIPC_CUDA_KNN_RC_FAR": "0"},                                                                          # never
     {"CWIPC_CUDA_KNN_SECOND_FROM_N": "0", "CWIPC_CUDA_KNN_PITCH": "0.6"},                                     # small pitch: most queries open
+    {"CWIPC_CUDA_KNN_RC_FAR": "0", "CWIPC_CUDA_KNN_PITCH": "0.4"},                                            # ... all of them through the tree search, started near the query
+    {"CWIPC_CUDA_KNN_RC_FAR": "0", "CWIPC_CUDA_KNN_PITCH": "0.4", "CWIPC_CUDA_KNN_FAR_START": "0"},           # ... and started at the root
 ])
 def test_knn_passes_split_the_work_not_the_result(cw, orc, env):
     """Main pass, second scan (knn_second_kernel) and tree search (knn_far_kernel) are three ways to the same exact
