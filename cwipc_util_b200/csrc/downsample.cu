@@ -574,6 +574,9 @@ struct StreamArgs {
     double res;
     OctreeBox *box_out;
     KeyTables *tables_out;        // the block-built tables, for the host-side diagnostics (may be null)
+    // $CWIPC_CUDA_DEBUG_STREAM: globaltimer stamps (ns) -- [0] first block start (min), [1] tables built (max), [2] last warp out of
+    // its tile loop (max), [3] last warp drained (max), [4] last block done, [5] sum and [6] count of the warps' tile-loop times
+    unsigned long long *dbg;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
@@ -859,7 +862,7 @@ __device__ __forceinline__ void lookup_leaf(const KeyTables *tab, float cx, floa
     *out = ls;
 }
 
-template <int MODE>
+template <int MODE, bool DBG = false> // DBG: per-phase time accounting of the tile loop (diagnostics build of the fused pass only)
 __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __grid_constant__ StreamArgs a, const __grid_constant__ KeyTables g_tab) {
     extern __shared__ __align__(128) unsigned char vs_smem_raw[];
     WarpStage *stages = reinterpret_cast<WarpStage *>(vs_smem_raw);
@@ -869,6 +872,12 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt(), le = lt | (1u << lane);
     WarpStage &ws = stages[warp];
+    auto now_ns = [] {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    };
+    if (a.dbg && threadIdx.x == 0) atomicMin(a.dbg + 0, now_ns());
 
     if (MODE == VS_TABLES) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&g_tab); // kernel parameter (constant bank) -> shared
@@ -895,6 +904,14 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
         for (uint32_t i = threadIdx.x; i < sizeof(KeyTables) / 4; i += VS_THREADS) dst[i] = src[i];
     }
 
+    __shared__ unsigned long long s_loop0[VS_WARPS]; // (diagnostics) kept out of the registers across the tile loop
+    __shared__ unsigned long long s_acc[DBG ? VS_WARPS : 1][8]; // DBG: ns per warp in [0] load wait [1] chunk box [2] run loop (with drains) [3] drains [4] join
+    if (DBG && lane == 0)
+        for (int i = 0; i < 8; i++) s_acc[warp][i] = 0;
+    if (a.dbg && lane == 0) {
+        s_loop0[warp] = now_ns();
+        if (warp == 0) atomicMax(a.dbg + 1, s_loop0[0]);
+    }
     const float inv = a.kp.inv;
     const uint32_t gw = blockIdx.x * VS_WARPS + warp, nw = gridDim.x * VS_WARPS;
     const Point16 *gpts = reinterpret_cast<const Point16 *>(a.pts);
@@ -910,7 +927,10 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
         dctx.header = a.header;
         dctx.slot_mask = a.slot_mask;
         dctx.claim_limit = a.claim_limit;
+        unsigned long long t0 = 0;
+        if (DBG) t0 = now_ns();
         seen_claims = drain_queue(qaddr, count, dctx, lane, seen_claims);
+        if (DBG && lane == 0) s_acc[warp][3] += now_ns() - t0;
     };
 
     // lane `lane` copies points c*32 + lane (c = 0..7) of a tile: 512 contiguous bytes per instruction.  Point i of the tile
@@ -934,8 +954,18 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
     for (; tile < a.ntiles; tile += nw, st ^= 1) {
         if (tile + nw < a.ntiles) issue(tile + nw, st ^ 1);
         cp_async_commit();
+        unsigned long long t_ph = 0;
+        if (DBG) t_ph = now_ns();
         cp_async_wait<1>();
         __syncwarp();
+        auto phase = [&](int i) { // DBG: time since the previous phase boundary goes to s_acc[warp][i]
+            if (DBG) {
+                const unsigned long long t = now_ns();
+                if (lane == 0) s_acc[warp][i] += t - t_ph;
+                t_ph = t;
+            }
+        };
+        phase(0);
 
         const uint32_t base = tile * VS_TILE;
         const uint32_t cnt = min((uint32_t)VS_TILE, a.n - base);
@@ -988,6 +1018,7 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
             }
         }
 
+        phase(1);
 #pragma unroll 2
         for (int j = 0; j < VS_L; j++) {
             if (qn > (uint32_t)(VS_QCAP - 32)) {
@@ -1060,6 +1091,7 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
             }
         }
 
+        phase(2);
         // ---- join the lanes' partial runs: a run that crosses lane boundaries is summed by a segmented scan ----
         const bool has_t = have;
         const bool single = has_t && nclosed == 0;          // the whole segment is one run
@@ -1097,9 +1129,19 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
         }
         qn += __popc(mh);
         __syncwarp();
+        phase(4);
     }
     cp_async_wait<0>();
+    if (DBG && a.dbg && lane == 0)
+        for (int i = 0; i < 5; i++) atomicAdd(a.dbg + 8 + i, s_acc[warp][i]);
+    if (a.dbg && lane == 0) {
+        const unsigned long long t = now_ns();
+        atomicMax(a.dbg + 2, t);
+        atomicAdd(a.dbg + 5, t - s_loop0[warp]);
+        atomicAdd(a.dbg + 6, 1ull);
+    }
     if (qn > 0) drain(qn);
+    if (a.dbg && lane == 0) atomicMax(a.dbg + 3, now_ns());
     if (bad) atomicOr(&a.header->error, 1u);
     if (amb) atomicOr(&a.header->pad[5], VS_FLAG_AMBIGUOUS);
 
@@ -1168,6 +1210,7 @@ __global__ void __launch_bounds__(VS_THREADS, 2) voxel_stream_kernel(const __gri
         unsigned long long t_tail1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_tail1));
         a.box_out->tail_ns = t_tail1 - t_tail0;
+        if (a.dbg) a.dbg[4] = t_tail1;
     }
 }
 
@@ -1441,6 +1484,14 @@ void launch_stream(const StreamArgs &args, const KeyTables &tab, int dev, cudaSt
     // persistent warps: two blocks of eight warps per SM, every warp takes tiles gw, gw + nw, ...
     static const size_t tiles_per_warp = [] { const char *e = getenv("CWIPC_CUDA_DS_TILES_PER_WARP"); return (size_t)std::max(1, e && *e ? atoi(e) : 1); }(); // tuning only
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up((size_t)args.ntiles, (size_t)VS_WARPS * tiles_per_warp), (size_t)sm_count(dev) * blocks_per_sm));
+    if constexpr (MODE == VS_FUSED) {
+        if (args.dbg) { // $CWIPC_CUDA_DEBUG_STREAM: the build with per-phase time accounting
+            CWCU_CHECK(cudaFuncSetAttribute(voxel_stream_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VS_SMEM_BYTES));
+            tune_kernel(voxel_stream_kernel<MODE, true>, carveout, true);
+            launch("voxel_stream_kernel", s, 16 * (size_t)args.n, [&] { voxel_stream_kernel<MODE, true><<<grid, VS_THREADS, VS_SMEM_BYTES, s>>>(args, tab); });
+            return;
+        }
+    }
     launch("voxel_stream_kernel", s, 16 * (size_t)args.n, [&] { voxel_stream_kernel<MODE><<<grid, VS_THREADS, VS_SMEM_BYTES, s>>>(args, tab); });
 }
 
@@ -1550,7 +1601,24 @@ DownsampleResult downsample_impl(const StoragePtr &in, float cellsize, bool octr
                 args.chunk_bbox = chunk_bbox.as<float>();
                 args.super_bbox = reinterpret_cast<uint32_t *>(wsp + ZW_HEADER_BYTES + capacity * sizeof(VoxelSlot));
                 args.box_out = box.as<OctreeBox>();
+                static const bool debug_stream = getenv("CWIPC_CUDA_DEBUG_STREAM") != nullptr;
+                Scratch dbg(debug_stream ? 16 * sizeof(unsigned long long) : 0, s);
+                if (debug_stream) {
+                    CWCU_CHECK(cudaMemsetAsync(dbg.p, 0, 16 * sizeof(unsigned long long), s));
+                    CWCU_CHECK(cudaMemsetAsync(dbg.p, 0xff, sizeof(unsigned long long), s));
+                    args.dbg = dbg.as<unsigned long long>();
+                }
                 launch_stream<VS_FUSED>(args, plan.tables, dev, s);
+                if (debug_stream) {
+                    unsigned long long h[16];
+                    CWCU_CHECK(cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+                    stream_sync(s);
+                    if (h[6])
+                        fprintf(stderr, "  per warp (mean us): load wait %.1f, chunk box %.1f, run loop %.1f of which drains %.1f, join %.1f (join's own drains are in both)\n", (double)h[8] / h[6] / 1e3,
+                                (double)h[9] / h[6] / 1e3, (double)h[10] / h[6] / 1e3, (double)h[11] / h[6] / 1e3, (double)h[12] / h[6] / 1e3);
+                    fprintf(stderr, "voxel_stream_kernel n=%zu: tables %.1f us, tile loops end %.1f (mean per warp %.1f), drained %.1f, last block done %.1f us after the first block started\n", n,
+                            (double)(h[1] - h[0]) / 1e3, (double)(h[2] - h[0]) / 1e3, h[6] ? (double)h[5] / (double)h[6] / 1e3 : 0.0, (double)(h[3] - h[0]) / 1e3, (double)(h[4] - h[0]) / 1e3);
+                }
             } else {
                 args.kp = plan.kp;
                 if (!octree_split) launch_stream<VS_LINEAR>(args, plan.tables, dev, s);

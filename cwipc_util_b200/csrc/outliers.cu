@@ -672,6 +672,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_second_kerne
 // through warp-shuffle bitonic networks.
 constexpr int KF_WARPS = 2;
 constexpr int KF_THREADS = KF_WARPS * 32;
+constexpr int KNN_MAX_K = 511; // k + 1 distances in at most 16 registers per lane of the tree search
 constexpr int KF_STACK = 416; // four nodes are expanded per step: <= 28 * top_level + 32 open nodes with top_level <= 13
 
 struct FarNode { // 20 B
@@ -707,6 +708,16 @@ __device__ __forceinline__ float warp_bitonic_merge32(float x, unsigned lane) { 
 // lives in lane e % 32, register e / 32.  Called by all 32 lanes of a warp with the same arguments.
 // One batch of up to 32 candidate distances into the lane-distributed sorted list (element e in lane e % 32,
 // register e / 32); returns the new kk-th smallest.
+// element e of a lane-distributed list (lane e % 32, register e / 32), e the same in every lane
+template <int KPL, class T>
+__device__ __forceinline__ T list_element(const T (&v)[KPL], int e) {
+    T x = v[0];
+#pragma unroll
+    for (int j = 1; j < KPL; j++)
+        if ((e >> 5) == j) x = v[j];
+    return __shfl_sync(FULL_MASK, x, e & 31);
+}
+
 template <int KPL>
 __device__ __forceinline__ float list_absorb(float (&v)[KPL], float d2, bool pass, unsigned pm, int kk, unsigned lane) {
     if (KPL == 1 && __popc(pm) <= 6) {
@@ -719,18 +730,30 @@ __device__ __forceinline__ float list_absorb(float (&v)[KPL], float d2, bool pas
             if (v[0] > x) v[0] = (lane == 0) ? x : fmaxf(up, x);
         }
     } else {
-        const float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
-        const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
+        float b = warp_bitonic_sort32(pass ? d2 : INFINITY, lane);
         if (KPL == 1) {
+            const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
             v[0] = warp_bitonic_merge32(fminf(v[0], r), lane);
-        } else {
+        } else if (KPL == 2) {
+            const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
             v[KPL - 1] = fminf(v[KPL - 1], r);
             const float lo = fminf(v[0], v[KPL - 1]), hi = fmaxf(v[0], v[KPL - 1]);
             v[0] = warp_bitonic_merge32(lo, lane);
             v[KPL - 1] = warp_bitonic_merge32(hi, lane);
+        } else {
+            // long lists (kNeighbors > 63): the sorted batch is merged into the registers front to back, each step keeping the 32
+            // smallest of (register, carry) and carrying the 32 largest on; registers that lie below the whole carry are skipped
+#pragma unroll
+            for (int j = 0; j < KPL; j++) {
+                if (__shfl_sync(FULL_MASK, b, 0) >= __shfl_sync(FULL_MASK, v[j], 31)) continue;
+                const float r = __shfl_sync(FULL_MASK, b, 31 - (int)lane);
+                const float lo = fminf(v[j], r), hi = fmaxf(v[j], r);
+                v[j] = warp_bitonic_merge32(lo, lane);
+                b = warp_bitonic_merge32(hi, lane);
+            }
         }
     }
-    return __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
+    return list_element<KPL>(v, kk - 1);
 }
 
 // Where a search starts: the root (level < 0), or the (at most) 2x2x2 nodes of `level` from (x, y, z) on, which are known to
@@ -875,6 +898,29 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
     }
 }
 
+// kNeighbors > 63 (lists too long for the main pass's per-lane registers): every query goes to the tree search.
+__global__ void __launch_bounds__(256) knn_queue_all_kernel(const uint64_t *__restrict__ sorted, uint32_t n, int idxbits, uint32_t nquery, FarEntry *__restrict__ far_list,
+                                                             uint32_t *__restrict__ far_count) {
+    const uint64_t idxmask = (1ull << idxbits) - 1ull;
+    const unsigned lane = lane_id();
+    const uint32_t rounds = (n + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+    for (uint32_t r = 0; r < rounds; r++) {
+        const uint32_t i = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        const bool query = i < n && (uint32_t)(sorted[i] & idxmask) < nquery;
+        const unsigned m = __ballot_sync(FULL_MASK, query);
+        if (m == 0u) continue;
+        uint32_t first = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) first = atomicAdd(far_count, (uint32_t)__popc(m));
+        first = __shfl_sync(FULL_MASK, first, __ffs(m) - 1);
+        if (query) {
+            FarEntry e;
+            e.q = i;
+            e.bound = INFINITY;
+            far_list[first + __popc(m & lanemask_lt())] = e;
+        }
+    }
+}
+
 // Start of the search for a query that is a point of the cloud itself (Morton code of its cell: `code`).  The smallest node
 // around its cell that holds kk points or more bounds the kk-th distance by the distance to that node's farthest corner
 // (one table entry per level, one level per lane); `limit` is lowered to that bound.  Every point within the bound then
@@ -969,11 +1015,8 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
 #pragma unroll
         for (int j = 0; j < KPL; j++) sq[j] = sqrt((double)v[j]);
         double sum = 0.0;
-        for (int e = 1; e <= k; e++) {
-            const double t = __shfl_sync(FULL_MASK, e < 32 ? sq[0] : sq[KPL - 1], e & 31);
-            sum += t;
-        }
-        const float kth = __shfl_sync(FULL_MASK, (kk - 1) < 32 ? v[0] : v[KPL - 1], (kk - 1) & 31);
+        for (int e = 1; e <= k; e++) sum += list_element<KPL>(sq, e);
+        const float kth = list_element<KPL>(v, kk - 1);
         if (lane == 0) {
             const size_t orig = (size_t)(sorted[ent.q] & idxmask);
             dist_out[orig] = (float)(sum / (double)k);
@@ -1317,6 +1360,21 @@ void run_knn(const cwipc_point *spts, const uint64_t *sorted, size_t n, const Gr
     });
 }
 
+// kNeighbors from 64 to KNN_MAX_K: no main pass, one tree search per query with a list of KPL registers per lane (slow path:
+// the reference has no limit on meanK, so large values must work, but no real caller uses them).
+template <int KPL>
+void run_knn_wide(const cwipc_point *spts, const uint64_t *sorted, size_t n, const GridParams &gp, int k, const uint2 *table, float *d_dist, float *d_kth, size_t nquery,
+                  FarEntry *far_list, uint32_t *far_count, int dev, cudaStream_t s) {
+    launch("knn_queue_all_kernel", s, 8 * n, [&] {
+        knn_queue_all_kernel<<<stream_grid(n, dev), 256, 0, s>>>(sorted, (uint32_t)n, gp.idxbits, (uint32_t)nquery, far_list, far_count);
+    });
+    launch("knn_far_kernel", s, (size_t)0, [&] {
+        static const bool far_start_on = env_float("CWIPC_CUDA_KNN_FAR_START", 1.f, 0.f, 1.f) != 0.f;
+        knn_far_kernel<KPL><<<(unsigned)sm_count(dev) * 8, KF_THREADS, 0, s>>>(spts, sorted, (uint32_t)n, gp, k + 1, k, table, d_dist, d_kth, far_list, far_count, 0xffffffffu, far_leaf_points(),
+                                                                               far_start_on);
+    });
+}
+
 // The search structure of one cloud: cell-ordered points + table pyramid (scratch lives as long as the object).
 struct KnnIndex {
     GridParams gp;
@@ -1368,7 +1426,7 @@ void build_index(KnnIndex &ix, const cwipc_point *in, size_t n, int k, float hin
 
 void check_k(int k, size_t n) {
     if (k < 1) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors must be >= 1"};
-    if (k + 1 > 64) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > 63 is not supported by libcwipc_util_cuda"};
+    if (k > KNN_MAX_K) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > " + std::to_string(KNN_MAX_K) + " is not supported by libcwipc_util_cuda"};
     (void)n;
 }
 
@@ -1389,10 +1447,17 @@ void knn_mean_distances_banded(const cwipc_point *in, size_t n, int k, float hin
         run_knn<decltype(kcap)::value>(ix.spts.as<cwipc_point>(), ix.sorted, n, ix.gp, k, ix.table.as<uint2>(), d_dist, d_kth, std::min(nquery, n), far_list.as<FarEntry>(),
                                        ix.far_count, dev, s);
     };
+    auto go_wide = [&](auto kpl) {
+        run_knn_wide<decltype(kpl)::value>(ix.spts.as<cwipc_point>(), ix.sorted, n, ix.gp, k, ix.table.as<uint2>(), d_dist, d_kth, std::min(nquery, n), far_list.as<FarEntry>(), ix.far_count,
+                                           dev, s);
+    };
     if (kk <= 8) go(std::integral_constant<int, 8>{});
     else if (kk <= 16) go(std::integral_constant<int, 16>{});
     else if (kk <= 32) go(std::integral_constant<int, 32>{});
-    else go(std::integral_constant<int, 64>{});
+    else if (kk <= 64) go(std::integral_constant<int, 64>{});
+    else if (kk <= 128) go_wide(std::integral_constant<int, 4>{});
+    else if (kk <= 256) go_wide(std::integral_constant<int, 8>{});
+    else go_wide(std::integral_constant<int, 16>{});
 }
 } // namespace
 
@@ -1415,10 +1480,15 @@ void knn_lists(const cwipc_point *in, size_t n, const cwipc_point *d_queries, co
     build_index(ix, in, n, k, hint_spacing, bounds, dev, s);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min(div_up(nq, (size_t)KF_WARPS), (size_t)sm_count(dev) * 8));
     launch("knn_list_kernel", s, (size_t)0, [&] {
-        if (kk <= 32)
-            knn_list_kernel<1><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, d_limits, (uint32_t)nq, d_lists, far_leaf_points());
-        else
-            knn_list_kernel<2><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, d_limits, (uint32_t)nq, d_lists, far_leaf_points());
+        auto go = [&](auto kpl) {
+            knn_list_kernel<decltype(kpl)::value><<<grid, KF_THREADS, 0, s>>>(ix.spts.as<cwipc_point>(), (uint32_t)n, ix.gp, kk, ix.table.as<uint2>(), d_queries, d_limits, (uint32_t)nq, d_lists,
+                                                                              far_leaf_points());
+        };
+        if (kk <= 32) go(std::integral_constant<int, 1>{});
+        else if (kk <= 64) go(std::integral_constant<int, 2>{});
+        else if (kk <= 128) go(std::integral_constant<int, 4>{});
+        else if (kk <= 256) go(std::integral_constant<int, 8>{});
+        else go(std::integral_constant<int, 16>{});
     });
 }
 

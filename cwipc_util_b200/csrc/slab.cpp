@@ -550,7 +550,7 @@ cwipc_pointcloud *cwipc_cuda_slab_remove_outliers(cwipc_pointcloud *pc, int kNei
     return slab_filter("cwipc_cuda_slab_remove_outliers", pc, comm, [&](const StoragePtr &in, int dev, cudaStream_t s) -> cwipc_pointcloud * {
         const size_t n = in->count;
         const float spacing = pc->cellsize();
-        if (kNeighbors + 1 > 64) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > 63 is not supported by libcwipc_util_cuda"};
+        if (kNeighbors > 511) throw CudaError{cudaErrorInvalidValue, "remove_outliers: kNeighbors > 511 is not supported by libcwipc_util_cuda"};
         StoragePtr out;
         if (!perTile) {
             out = std::make_shared<Storage>(dev, n, s);

@@ -400,6 +400,30 @@ def test_knn_mostly_far_queries_and_dense_cells(cw, orc):
         assert np.array_equal(cw.util.knn_mean_distances(upload(cw, pts, cellsize=cellsize), 30), want), cellsize
 
 
+@pytest.mark.parametrize("k", [64, 65, 100, 127, 128, 200, 255, 256, 400, 511])
+def test_knn_long_lists(cw, orc, k):
+    """kNeighbors above 63 (the reference has no limit on meanK): no main pass, one tree search per query with the k+1
+    distances in 4 / 8 / 16 registers per lane -- the same exact distances, the same summation order."""
+    pts = synthetic.add_outliers(synthetic.camera_cloud(6000, seed=k), 0.02, seed=k)
+    assert np.array_equal(cw.util.knn_mean_distances(upload(cw, pts, cellsize=0.008), k), orc.knn_mean_distances(pts, k))
+
+
+def test_remove_outliers_long_lists(cw, orc):
+    from parity_helpers import per_tile_check
+    pts = synthetic.camera_cloud(30000, seed=17)
+    for k in (100, 300):
+        want, _ = orc.remove_outliers(pts, k, 1.0, False)
+        got = download(cw.cwipc_remove_outliers(upload(cw, pts), k, 1.0, False))
+        if not np.array_equal(got, want):
+            keepmask_check(pts, got, orc.knn_mean_distances(pts, k), k, 1.0)
+    per_tile_check(orc, pts, download(cw.cwipc_remove_outliers(upload(cw, pts), 100, 1.0, True)), 100, 1.0)
+    cw.cwipc_log_configure(cw.CWIPC_LOG_LEVEL_NONE, lambda level, msg: None)
+    try:   # beyond the longest list the call is refused, loudly
+        assert not cw.util.cwipc_util_dll_load().cwipc_remove_outliers(upload(cw, pts).as_cwipc_p(), 512, 1.0, False)
+    finally:
+        cw.cwipc_log_configure(cw.CWIPC_LOG_LEVEL_WARNING, None)
+
+
 @pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 64, 65, 1000])
 def test_knn_tiny_clouds(cw, orc, n):
     pts = random_cloud(n, seed=n, extent=0.1)
