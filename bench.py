@@ -36,7 +36,7 @@ import time
 
 import numpy as np
 
-# 15 streams per GPU: more hardware queues than the default 8 (must be set before the CUDA context exists)
+# 30 streams per GPU: more hardware queues than the default 8 (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -47,7 +47,8 @@ VOXEL = 0.01
 K, STDDEV = int(os.environ.get("BENCH_K", 30)), 1.0   # BENCH_K: diagnostic only
 SEQUENCE_FRAMES = 240        # configs[4]: the whole sequence, split over the GPUs
 PASSES = 8                   # passes over the sequence per step
-WORKERS = 15                 # host threads (one CUDA stream each) feeding one GPU; divides the 30 frames of a step
+WORKERS = 30                 # host threads (one CUDA stream each) feeding one GPU; divides the rank's share of the 240 frames at 1, 2 and 4 GPUs
+                             # (scripts/ab_value.py on one B200, 16 host cores: 15 threads 8.2-8.5, 24 threads 8.3-8.6, 32 threads 8.6-8.7 Gpoints/s)
 HBM_FALLBACK_GBS = 6650.0    # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -451,10 +452,10 @@ def run_ours(args):
     os.dup2(2, 1)
     world, rank, local, dist, torch = dist_setup(args)
     # Host threads: each worker spends most of its time waiting for a count readback; the library polls briefly and
-    # then naps between polls (csrc/runtime.cu: stream_sync), so 15 threads per GPU also work on 4 cores per GPU.
+    # then naps between polls (csrc/runtime.cu: stream_sync), so many threads per GPU also work on few cores per GPU.
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if args.workers <= 0:
-        args.workers = WORKERS
+        args.workers = WORKERS if cores >= world * 16 else 15   # 30 threads with 16 cores or more per rank, else 15
         if cores < world * 8:
             # e.g. 8 ranks on a 32-core node: fewer, lazier waiters (measured at 8 GPUs: 10 threads napping 60 us
             # gave 42.6 Gpoints/s, 15 napping 20 us 39.7, 10 polling 36.5)

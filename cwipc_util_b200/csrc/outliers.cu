@@ -872,6 +872,17 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
         const int node_level = (int)(node.zl >> 16);
         sp -= take;
         __syncwarp();
+        // Sparse neighbourhoods (an isolated point among other isolated points: one or two points per node): when none of the
+        // nodes taken holds more than eight points they are scanned together, eight lanes per node, in one pass.
+        if (__all_sync(FULL_MASK, !have || node.pe - node.pb <= 8u)) {
+            const uint32_t c = node.pb + (lane & 7u);
+            float d2 = INFINITY;
+            if (have && c < node.pe && !(node.mind2 * 0.9999f > fminf(tau, limit))) d2 = dist2(q, spts16[c]);
+            const bool pass = d2 < tau && d2 <= limit;
+            const unsigned pm = __ballot_sync(FULL_MASK, pass);
+            if (pm) tau = list_absorb<KPL>(v, d2, pass, pm, kk, lane);
+            continue;
+        }
         // small nodes first (nearest first): scanning them tightens the bound for the expansions below
         for (int j = 0; j < take; j++) {
             const uint32_t pb = __shfl_sync(FULL_MASK, node.pb, j * 8), pe = __shfl_sync(FULL_MASK, node.pe, j * 8);

@@ -278,6 +278,8 @@ _CWIPC_UTIL_EXPORT cwipc_activesource *cwipc_proxy(const char *host, int port, c
 /* THE HOT PATH: filters.  Input is borrowed and never modified; the result is a new device-resident
  * cloud owned by the caller.  NULL input gives NULL. */
 _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_downsample(cwipc_pointcloud *pc, float voxelsize);  /* ref: api.h:1063, src/cwipc_filters.cpp:30-172 */
+/* kNeighbors: 1..63 takes the fast path (lists in registers), 64..511 a slower exact path (one tree search per point); larger
+ * values return NULL with an ERROR log (the reference, pcl::StatisticalOutlierRemoval::setMeanK, has no limit). */
 _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_remove_outliers(cwipc_pointcloud *pc, int kNeighbors, float stddevMulThresh, bool perTile); /* ref: api.h:1075, src/cwipc_filters.cpp:181-278 */
 _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_tilefilter(cwipc_pointcloud *pc, int tile);         /* ref: api.h:1085, src/cwipc_filters.cpp:281-306 */
 _CWIPC_UTIL_EXPORT cwipc_pointcloud *cwipc_tilemap(cwipc_pointcloud *pc, uint8_t map[256]);    /* ref: api.h:1096, src/cwipc_filters.cpp:308-331 */
