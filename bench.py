@@ -521,6 +521,7 @@ def run_ours(args):
     dist_barrier(dist, torch)
     # the path an UNCHANGED reference caller takes: cwipc_from_points from its own pageable memory (python/cwipc/util.py
     # passes ctypes / numpy buffers), one step of one pass
+    run_steps(workers, barrier, state, lib, "e2e_pageable", 1, passes=1)     # warm-up: every thread's staging ring gets allocated here
     pageable_ms = run_steps(workers, barrier, state, lib, "e2e_pageable", 1, passes=1)
     dist_barrier(dist, torch)
 
