@@ -383,11 +383,19 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_tile_kernel(
                 const uint32_t cnt = min((uint32_t)KT_CH, total - chunk * KT_CH);
                 const bool last_chunk = chunk + 1 == nchunks;
                 for (uint32_t c = 0; c < cnt; c += 4) {
+                    if (c + 4 <= cnt) { // (all but the last step of the last chunk: no per-candidate bound check)
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (c + u < cnt) {
+                        for (int u = 0; u < 4; u++) {
                             const Point16 cand = ws.cand[st][c + u]; // same address in every lane: one broadcast load
                             const float d2 = dist2(q, cand);
+                            if (d2 < tau) {
+                                ws.buf[bcnt][lane] = d2;
+                                bcnt++;
+                            }
+                        }
+                    } else {
+                        for (uint32_t u = c; u < cnt; u++) {
+                            const float d2 = dist2(q, ws.cand[st][u]);
                             if (d2 < tau) {
                                 ws.buf[bcnt][lane] = d2;
                                 bcnt++;
@@ -614,11 +622,19 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_second_kerne
                     const uint32_t cnt = min((uint32_t)KT_CH, total - chunk * KT_CH);
                     const bool last_chunk = chunk + 1 == nchunks;
                     for (uint32_t c = 0; c < cnt; c += 4) {
+                        if (c + 4 <= cnt) {
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            if (c + u < cnt) {
+                            for (int u = 0; u < 4; u++) {
                                 const Point16 cand = ws.cand[st][c + u];
                                 const float d2 = dist2(q, cand);
+                                if (d2 < tau) {
+                                    ws.buf[bcnt][lane] = d2;
+                                    bcnt++;
+                                }
+                            }
+                        } else {
+                            for (uint32_t u = c; u < cnt; u++) {
+                                const float d2 = dist2(q, ws.cand[st][u]);
                                 if (d2 < tau) {
                                     ws.buf[bcnt][lane] = d2;
                                     bcnt++;
