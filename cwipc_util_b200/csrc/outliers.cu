@@ -689,9 +689,11 @@ __global__ void __launch_bounds__(KT_THREADS, KT_BLOCKS_PER_SM) knn_second_kerne
 constexpr int KF_WARPS = 2;
 constexpr int KF_THREADS = KF_WARPS * 32;
 constexpr int KNN_MAX_K = 511; // k + 1 distances in at most 16 registers per lane of the tree search
-constexpr int KF_STACK = 416; // four nodes are expanded per step: <= 28 * top_level + 32 open nodes with top_level <= 13
 
-struct FarNode { // 20 B
+constexpr int KF_STACK = 416; // four nodes are expanded per step: <= 28 * top_level + 32 open nodes with top_level <= 13
+static_assert(KF_STACK * 20 >= 16 * 32 * 8 && (KF_STACK * 20) % 16 == 0, "the stack doubles as the buffer of square roots");
+
+struct FarNode { // 20 B (the stack of one warp, KF_STACK of them, also holds the 32 * KPL <= 512 square roots of a finished search)
     uint32_t pb, pe;  // point range
     uint32_t xy;      // node coordinates at its level: x | y << 16
     uint32_t zl;      // z | level << 16
@@ -900,12 +902,15 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
             continue;
         }
         // small nodes first (nearest first): scanning them tightens the bound for the expansions below
-        for (int j = 0; j < take; j++) {
-            const uint32_t pb = __shfl_sync(FULL_MASK, node.pb, j * 8), pe = __shfl_sync(FULL_MASK, node.pe, j * 8);
-            const int level = __shfl_sync(FULL_MASK, node_level, j * 8);
-            const float nm = __shfl_sync(FULL_MASK, node.mind2, j * 8);
-            if (!(level == 0 || pe - pb <= leaf_points)) continue;
-            if (nm * 0.9999f > fminf(tau, limit)) continue;
+        const bool is_leaf = node_level == 0 || node.pe - node.pb <= leaf_points;
+        // the groups' first lanes (0, 8, 16, 24) vote for their nodes: only nodes that are scanned cost anything here
+        unsigned todo = __ballot_sync(FULL_MASK, have && is_leaf && !(node.mind2 * 0.9999f > fminf(tau, limit))) & 0x01010101u;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t pb = __shfl_sync(FULL_MASK, node.pb, src), pe = __shfl_sync(FULL_MASK, node.pe, src);
+            const float nm = __shfl_sync(FULL_MASK, node.mind2, src);
+            if (nm * 0.9999f > fminf(tau, limit)) continue; // (the bound may have dropped since the vote)
             for (uint32_t base = pb; base < pe; base += 32) {
                 const uint32_t c = base + lane;
                 float d2 = INFINITY;
@@ -917,7 +922,7 @@ __device__ __forceinline__ void dfs_knn(const Point16 q, float limit, const Poin
         }
         // the others: one child per lane
         const float thr = fminf(tau, limit);
-        const bool expand = have && !(node_level == 0 || node.pe - node.pb <= leaf_points) && !(node.mind2 * 0.9999f > thr);
+        const bool expand = have && !is_leaf && !(node.mind2 * 0.9999f > thr);
         const int cl = node_level - 1;
         const uint32_t chx = 2u * node_x + ((lane >> 2) & 1u), chy = 2u * node_y + ((lane >> 1) & 1u), chz = 2u * node_z + (lane & 1u);
         push_nodes(expand, cl, chx, chy, chz, thr);
@@ -1013,7 +1018,7 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
                                                               const uint2 *__restrict__ table, float *__restrict__ dist_out, float *__restrict__ kth_out,
                                                               const FarEntry *__restrict__ far_list, const uint32_t *__restrict__ far_count, uint32_t second_from,
                                                               uint32_t leaf_points, bool far_start_enabled) {
-    __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
+    __shared__ __align__(16) FarNode s_stack[KF_WARPS][KF_STACK]; // (also holds 32 * KPL doubles per warp at the end of a search)
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     // when the second scan ran (the main pass queued at least second_from queries) the list it passed on is the one to
     // take: it lies (n + 64) entries behind the main pass's, its counter one word behind
@@ -1041,9 +1046,16 @@ __global__ void __launch_bounds__(KF_THREADS) knn_far_kernel(const cwipc_point *
         double sq[KPL];
 #pragma unroll
         for (int j = 0; j < KPL; j++) sq[j] = sqrt((double)v[j]);
+        // the square roots go through the (now idle) stack memory: every lane adds them up in ascending order from there
+        double *s_sq = reinterpret_cast<double *>(s_stack[warp]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < KPL; j++) s_sq[j * 32 + (int)lane] = sq[j];
+        __syncwarp();
         double sum = 0.0;
-        for (int e = 1; e <= k; e++) sum += list_element<KPL>(sq, e);
+        for (int e = 1; e <= k; e++) sum += s_sq[e];
         const float kth = list_element<KPL>(v, kk - 1);
+        __syncwarp(); // the stack is written again by the next search
         if (lane == 0) {
             const size_t orig = (size_t)(sorted[ent.q] & idxmask);
             dist_out[orig] = (float)(sum / (double)k);
@@ -1058,7 +1070,7 @@ template <int KPL>
 __global__ void __launch_bounds__(KF_THREADS) knn_list_kernel(const cwipc_point *__restrict__ spts, uint32_t n, GridParams gp, int kk, const uint2 *__restrict__ table,
                                                                const cwipc_point *__restrict__ queries, const float *__restrict__ limits, uint32_t nq, float *__restrict__ lists,
                                                                uint32_t leaf_points) {
-    __shared__ FarNode s_stack[KF_WARPS][KF_STACK];
+    __shared__ __align__(16) FarNode s_stack[KF_WARPS][KF_STACK]; // (also holds 32 * KPL doubles per warp at the end of a search)
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const Point16 *spts16 = reinterpret_cast<const Point16 *>(spts);
