@@ -108,7 +108,21 @@ struct ThreadState {
         bool pending[STAGE_SLOTS] = {false, false, false, false};
         unsigned next = 0;
     } stage;
+    static std::mutex &idle_stage_mu() { static std::mutex *m = new std::mutex; return *m; }           // (never destroyed: threads may
+    static std::vector<Stage> &idle_stages() { static auto *v = new std::vector<Stage>; return *v; }  //  exit after main returns)
     ~ThreadState() {
+        // the staging ring (8 MB of page-locked memory) goes back to a process-wide list, so that hosts which start a thread per
+        // frame do not pin more and more memory; its transfers are waited for first (errors ignored: CUDA may be shutting down)
+        if (stage.ring) {
+            for (int i = 0; i < STAGE_SLOTS; i++) {
+                if (stage.pending[i] && stage.done[i]) (void)cudaEventSynchronize(stage.done[i]);
+                stage.pending[i] = false;
+            }
+            (void)cudaGetLastError();
+            std::lock_guard<std::mutex> lk(idle_stage_mu());
+            idle_stages().push_back(stage);
+            stage.ring = nullptr;
+        }
         // give streams back so that thread churn does not leak them
         if (g_devs) {
             for (size_t d = 0; d < streams.size(); d++) {
@@ -408,10 +422,20 @@ struct StageRing {
     ThreadState::Stage &st;
     int dev;
     explicit StageRing(int dev_) : st(t_state.stage), dev(dev_) {
-        if (!st.ring) {
-            void *p = nullptr;
-            CWCU_CHECK(cudaHostAlloc(&p, ThreadState::STAGE_SLOTS * ThreadState::STAGE_CHUNK, cudaHostAllocPortable));
-            st.ring = static_cast<char *>(p);
+        if (!st.ring) { // adopt a ring an exited thread left behind, else pin a new one
+            {
+                std::lock_guard<std::mutex> lk(ThreadState::idle_stage_mu());
+                auto &idle = ThreadState::idle_stages();
+                if (!idle.empty()) {
+                    st = idle.back();
+                    idle.pop_back();
+                }
+            }
+            if (!st.ring) {
+                void *p = nullptr;
+                CWCU_CHECK(cudaHostAlloc(&p, ThreadState::STAGE_SLOTS * ThreadState::STAGE_CHUNK, cudaHostAllocPortable));
+                st.ring = static_cast<char *>(p);
+            }
         }
     }
     char *slot(int i) const { return st.ring + (size_t)i * ThreadState::STAGE_CHUNK; }

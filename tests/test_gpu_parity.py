@@ -106,6 +106,13 @@ def test_pageable_copies_through_the_staging_ring(cw):
     for t in threads:
         t.join()
     assert not errors, errors
+    # short-lived threads, one after the other (a host that starts a thread per frame): each adopts the ring its predecessor
+    # left behind instead of pinning another 8 MB
+    for i in range(6):
+        t = threading.Thread(target=worker, args=(10 + i,))
+        t.start()
+        t.join()
+    assert not errors, errors
 
 
 def test_from_points_size_mismatch_raises(cw, lib):
