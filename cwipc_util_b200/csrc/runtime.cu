@@ -460,11 +460,27 @@ struct StageRing {
 };
 } // namespace
 
+// what the CUDA runtime knows about a caller's pointer: page-locked host memory, memory the driver addresses itself
+// (device or managed), or ordinary host memory
+enum class HostKind { Pageable, Pinned, DriverAddressable };
+static HostKind host_kind(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return HostKind::Pageable;
+    }
+    if (attr.type == cudaMemoryTypeHost) return HostKind::Pinned;
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return HostKind::DriverAddressable;
+    return HostKind::Pageable;
+}
+
 bool copy_from_host(void *dst, const void *src, size_t bytes, cudaStream_t s) {
     if (bytes == 0) return false;
-    const bool pinned = is_pinned_host(src);
-    if (pinned || bytes < STAGE_MIN_BYTES || !staging_enabled()) {
-        CWCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    const HostKind kind = host_kind(src);
+    const bool pinned = kind == HostKind::Pinned;
+    if (kind != HostKind::Pageable || bytes < STAGE_MIN_BYTES || !staging_enabled()) {
+        // (a device or managed pointer is the driver's business: never touched by the host-side memcpy below)
+        CWCU_CHECK(cudaMemcpyAsync(dst, src, bytes, kind == HostKind::DriverAddressable ? cudaMemcpyDefault : cudaMemcpyHostToDevice, s));
         return pinned;
     }
     int dev = 0;
@@ -484,8 +500,9 @@ bool copy_from_host(void *dst, const void *src, size_t bytes, cudaStream_t s) {
 
 void copy_to_host(void *dst, const void *src, size_t bytes, cudaStream_t s) {
     if (bytes == 0) return;
-    if (bytes < STAGE_MIN_BYTES || !staging_enabled() || is_pinned_host(dst)) {
-        CWCU_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    const HostKind kind = (bytes < STAGE_MIN_BYTES || !staging_enabled()) ? HostKind::Pinned : host_kind(dst);
+    if (kind != HostKind::Pageable) {
+        CWCU_CHECK(cudaMemcpyAsync(dst, src, bytes, kind == HostKind::DriverAddressable ? cudaMemcpyDefault : cudaMemcpyDeviceToHost, s));
         stream_sync(s);
         return;
     }
