@@ -18,8 +18,13 @@
 //                       by TMA bulk copies (one per cell range, double buffered); per lane an adaptive
 //                       threshold + bitonic merge keeps the k+1 smallest distances in sorted registers.
 //                       A query is final when its (k+1)-th distance is within Rc pitches; the rest is queued.
+//   knn_second_kernel   (clouds of 256 K points and more) the queued queries of a group that lie side by side are
+//                       scanned once more over the cells within their own bound, lanes = queries as above.
 //   knn_far_kernel      one warp per queued query: depth-first search of the table pyramid (an implicit
-//                       octree), four nearest open nodes per step, pruned by the running (k+1)-th best.
+//                       octree), four nearest open nodes per step, pruned by the running (k+1)-th best.  The
+//                       search starts at the <= 2x2x2 nodes around the query that cover the ball of a first
+//                       bound (farthest corner of the smallest node around its cell that holds k+1 points).
+//                       kNeighbors 64..511: no main pass, this kernel alone, lists of 4/8/16 registers per lane.
 //   stats_kernel        sum d, sum (float)(d*d) in double, fixed two-level order (deterministic)
 //   compact_kernel      keep mask + stable compaction (pointops.cu)
 // Exactness never depends on the grid pitch; the pitch only moves work between the two passes.
