@@ -1,3 +1,5 @@
+# A/B of the voxel list in 64 segments with a counter each (CWIPC_CUDA_DS_COUNTERS): measured, no gain, NOT kept -- the knob no longer exists;
+# the output is profiles/r02z_ab_threads_counters.txt
 TAG=${1:-r02z5}
 OUT=gpurun_out/ab_${TAG}.txt
 : > $OUT
